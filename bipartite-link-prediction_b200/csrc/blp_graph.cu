@@ -1,0 +1,285 @@
+// Graph handle: de-duplicated bipartite adjacency as two padded CSR arrays resident in HBM.
+// Replaces snap.LoadEdgeList / snap.Nodes / GetNI().GetDeg() of the reference
+// (similarity.py:16, 22, 65, 121).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "blp_internal.h"
+
+namespace blp {
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e),
+             file, line, what);
+    g_last_error = buf;
+    // clear the sticky-less error so that the next call starts clean
+    (void)cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? BLP_ERR_OOM : BLP_ERR_CUDA;
+}
+
+template <typename T>
+static int upload(T** dptr, const std::vector<T>& h, int64_t* bytes) {
+    size_t n = h.size() * sizeof(T);
+    BLP_CUDA_TRY(cudaMalloc((void**)dptr, n ? n : sizeof(T)));
+    if (n) BLP_CUDA_TRY(cudaMemcpy(*dptr, h.data(), n, cudaMemcpyHostToDevice));
+    *bytes += (int64_t)n;
+    return BLP_OK;
+}
+
+// Least-significant-digit radix sort of 64-bit keys on the host, only over the bits in use.
+static void radix_sort_u64(std::vector<uint64_t>& keys, int bits_used) {
+    const int RB = 11;
+    const size_t n = keys.size();
+    std::vector<uint64_t> tmp(n);
+    std::vector<size_t> cnt((size_t)1 << RB);
+    uint64_t* src = keys.data();
+    uint64_t* dst = tmp.data();
+    for (int shift = 0; shift < bits_used; shift += RB) {
+        std::fill(cnt.begin(), cnt.end(), 0);
+        const uint64_t mask = ((uint64_t)1 << RB) - 1;
+        for (size_t i = 0; i < n; ++i) cnt[(src[i] >> shift) & mask]++;
+        size_t run = 0;
+        for (size_t d = 0; d < cnt.size(); ++d) {
+            size_t c = cnt[d];
+            cnt[d] = run;
+            run += c;
+        }
+        for (size_t i = 0; i < n; ++i) dst[cnt[(src[i] >> shift) & mask]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != keys.data()) memcpy(keys.data(), src, n * sizeof(uint64_t));
+}
+
+static int bits_for(uint64_t v) {
+    int b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return b ? b : 1;
+}
+
+// Row offsets of one padded CSR direction (each row rounded up to a multiple of four ids).
+static void padded_offsets(int32_t n_rows, const std::vector<int32_t>& deg,
+                           std::vector<long long>& off) {
+    off.assign((size_t)n_rows + 1, 0);
+    for (int32_t r = 0; r < n_rows; ++r) off[r + 1] = off[r] + (((long long)deg[r] + 3) & ~3LL);
+}
+
+static void weights_from_degrees(const std::vector<int32_t>& deg, int32_t max_deg,
+                                 std::vector<long long>& w) {
+    // 1/ln(deg) once per distinct degree with the host libm (the kernels do no transcendental
+    // math), rounded to Q24.40.  deg <= 1 contributes 0 (similarity.py:122-125).
+    std::vector<long long> lut((size_t)max_deg + 1, 0);
+    for (int32_t d = 2; d <= max_deg; ++d)
+        lut[d] = llrint(ldexp(1.0 / log((double)d), BLP_AA_FRAC_BITS));
+    w.resize(deg.size());
+    for (size_t i = 0; i < deg.size(); ++i) w[i] = lut[deg[i]];
+}
+}  // namespace blp
+
+extern "C" int blp_version(void) { return BLP_VERSION; }
+
+extern "C" const char* blp_last_error(void) { return blp::g_last_error.c_str(); }
+
+extern "C" int blp_device_count(int* count) {
+    if (!count) {
+        blp::set_error("blp_device_count: null argument");
+        return BLP_ERR_INVALID;
+    }
+    *count = 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        blp::set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+        return BLP_ERR_CUDA;
+    }
+    *count = n;
+    return BLP_OK;
+}
+
+extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
+                                const int32_t* edge_u, const int32_t* edge_b, int device,
+                                blp_graph** out) {
+    if (!out) {
+        blp::set_error("blp_graph_create: out is null");
+        return BLP_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (n_users <= 0 || n_biz <= 0 || n_edges < 0 || (n_edges > 0 && (!edge_u || !edge_b))) {
+        blp::set_error("blp_graph_create: need n_users>0, n_biz>0, n_edges>=0 and edge arrays");
+        return BLP_ERR_INVALID;
+    }
+    int ndev = 0;
+    int rc = blp_device_count(&ndev);
+    if (rc != BLP_OK) return rc;
+    if (device < 0 || device >= ndev) {
+        blp::set_error("blp_graph_create: device index out of range");
+        return BLP_ERR_INVALID;
+    }
+    BLP_CUDA_TRY(cudaSetDevice(device));
+
+    blp_graph* g = nullptr;
+    try {
+        // ---- de-duplicate: sort (u,b) keys, keep one of each (SNAP TUNGraph ignores repeats)
+        const int bb = blp::bits_for((uint64_t)n_biz);      // key = u << bb | b, bits in use only
+        const uint64_t bmask = ((uint64_t)1 << bb) - 1;
+        std::vector<uint64_t> keys((size_t)n_edges);
+        for (int64_t i = 0; i < n_edges; ++i) {
+            int32_t u = edge_u[i], b = edge_b[i];
+            if (u < 0 || u >= n_users || b < 0 || b >= n_biz) {
+                char buf[160];
+                snprintf(buf, sizeof(buf),
+                         "blp_graph_create: edge %lld = (%d,%d) outside [0,%d) x [0,%d)",
+                         (long long)i, u, b, n_users, n_biz);
+                blp::set_error(buf);
+                return BLP_ERR_RANGE;
+            }
+            keys[i] = ((uint64_t)(uint32_t)u << bb) | (uint32_t)b;
+        }
+        if (n_edges > (1 << 16))
+            blp::radix_sort_u64(keys, bb + blp::bits_for((uint64_t)n_users));
+        else
+            std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        const size_t m = keys.size();
+
+        std::vector<int32_t> u_deg((size_t)n_users, 0), b_deg((size_t)n_biz, 0);
+        for (size_t i = 0; i < m; ++i) {
+            u_deg[keys[i] >> bb]++;
+            b_deg[keys[i] & bmask]++;
+        }
+        std::vector<long long> u_off, b_off;
+        blp::padded_offsets(n_users, u_deg, u_off);
+        blp::padded_offsets(n_biz, b_deg, b_off);
+        std::vector<int32_t> u_adj((size_t)u_off[n_users], n_biz);   // pre-filled with sentinels
+        std::vector<int32_t> b_adj((size_t)b_off[n_biz], n_users);
+        {
+            // keys ascend by (u,b): user rows fill in order; business rows receive users in
+            // ascending order too, so both directions come out sorted.
+            std::vector<long long> bcur(b_off.begin(), b_off.end() - 1);
+            size_t i = 0;
+            for (int32_t u = 0; u < n_users; ++u) {
+                long long w = u_off[u];
+                for (int32_t k = 0; k < u_deg[u]; ++k, ++i) {
+                    int32_t b = (int32_t)(keys[i] & bmask);
+                    u_adj[w++] = b;
+                    b_adj[bcur[b]++] = u;
+                }
+            }
+        }
+        std::vector<uint64_t>().swap(keys);
+
+        g = new blp_graph();
+        g->device = device;
+        g->n_users = n_users;
+        g->n_biz = n_biz;
+        g->n_edges_in = n_edges;
+        g->n_edges = (int64_t)m;
+        for (int32_t d : u_deg) {
+            g->n_users_in += d > 0;
+            g->max_udeg = std::max(g->max_udeg, d);
+        }
+        for (int32_t d : b_deg) {
+            g->n_biz_in += d > 0;
+            g->max_bdeg = std::max(g->max_bdeg, d);
+        }
+        std::vector<long long> u_w, b_w;
+        blp::weights_from_degrees(u_deg, g->max_udeg, u_w);
+        blp::weights_from_degrees(b_deg, g->max_bdeg, b_w);
+
+        cudaDeviceProp prop;
+        rc = BLP_OK;
+        cudaError_t e = cudaGetDeviceProperties(&prop, device);
+        if (e != cudaSuccess) rc = blp::cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__);
+        if (rc == BLP_OK) {
+            g->sm_count = prop.multiProcessorCount;
+            g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+        }
+        if (rc == BLP_OK) rc = blp::upload(&g->u_off, u_off, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->b_off, b_off, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->u_adj, u_adj, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->b_adj, b_adj, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->u_deg, u_deg, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->b_deg, b_deg, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->u_w, u_w, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->b_w, b_w, &g->device_bytes);
+        if (rc != BLP_OK) {
+            std::string keep = blp_last_error();
+            blp_graph_destroy(g);
+            blp::set_error(keep);
+            return rc;
+        }
+    } catch (const std::bad_alloc&) {
+        if (g) blp_graph_destroy(g);
+        blp::set_error("blp_graph_create: host allocation failed");
+        return BLP_ERR_OOM;
+    }
+    *out = g;
+    return BLP_OK;
+}
+
+extern "C" int blp_graph_destroy(blp_graph* g) {
+    if (!g) return BLP_OK;
+    cudaSetDevice(g->device);
+    cudaFree(g->u_off);
+    cudaFree(g->b_off);
+    cudaFree(g->u_adj);
+    cudaFree(g->b_adj);
+    cudaFree(g->u_deg);
+    cudaFree(g->b_deg);
+    cudaFree(g->u_w);
+    cudaFree(g->b_w);
+    (void)cudaGetLastError();
+    delete g;
+    return BLP_OK;
+}
+
+extern "C" int blp_graph_info(const blp_graph* g, blp_graph_info_t* info) {
+    if (!g || !info) {
+        blp::set_error("blp_graph_info: null argument");
+        return BLP_ERR_INVALID;
+    }
+    info->n_users = g->n_users;
+    info->n_biz = g->n_biz;
+    info->n_edges_in = g->n_edges_in;
+    info->n_edges = g->n_edges;
+    info->n_users_in_graph = g->n_users_in;
+    info->n_biz_in_graph = g->n_biz_in;
+    info->max_user_degree = g->max_udeg;
+    info->max_biz_degree = g->max_bdeg;
+    info->device_bytes = g->device_bytes;
+    info->device = g->device;
+    info->sm_count = g->sm_count;
+    return BLP_OK;
+}
+
+extern "C" int blp_graph_degrees(const blp_graph* g, int side, int32_t* host_out) {
+    if (!g || !host_out || (side != BLP_SIDE_USER && side != BLP_SIDE_BUSINESS)) {
+        blp::set_error("blp_graph_degrees: bad argument");
+        return BLP_ERR_INVALID;
+    }
+    BLP_CUDA_TRY(cudaSetDevice(g->device));
+    const int* src = side == BLP_SIDE_USER ? g->u_deg : g->b_deg;
+    size_t n = (size_t)(side == BLP_SIDE_USER ? g->n_users : g->n_biz);
+    BLP_CUDA_TRY(cudaMemcpy(host_out, src, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return BLP_OK;
+}
+
+extern "C" int blp_score_stats(const blp_graph* g, int side, blp_score_stats_t* stats) {
+    if (!g || !stats || (side != BLP_SIDE_USER && side != BLP_SIDE_BUSINESS)) {
+        blp::set_error("blp_score_stats: bad argument");
+        return BLP_ERR_INVALID;
+    }
+    *stats = g->stats[side];
+    return BLP_OK;
+}

@@ -1,0 +1,47 @@
+// Internal declarations shared by the graph builder and the scoring kernels (not part of the ABI).
+#ifndef BLP_INTERNAL_H_
+#define BLP_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "blp.h"
+
+// Q24.40 fixed point for the Adamic-Adar weights: integer sums are order independent.
+#define BLP_AA_FRAC_BITS 40
+
+struct blp_graph {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;  // bytes of dynamic shared memory one CTA may opt in to
+    int32_t n_users = 0, n_biz = 0;
+    int64_t n_edges_in = 0, n_edges = 0;
+    int32_t n_users_in = 0, n_biz_in = 0, max_udeg = 0, max_bdeg = 0;
+    int64_t device_bytes = 0;
+    // Both CSR directions.  Row offsets count PADDED entries: every row is padded to a multiple of
+    // four ids with the sentinel n_biz (user rows) / n_users (business rows), so every row starts
+    // 16-byte aligned and is read with 128-bit loads without a tail.
+    long long* u_off = nullptr;  // [n_users+1]
+    long long* b_off = nullptr;  // [n_biz+1]
+    int* u_adj = nullptr;        // user -> businesses, ascending
+    int* b_adj = nullptr;        // business -> users, ascending
+    int* u_deg = nullptr;        // true (unpadded, de-duplicated) degrees
+    int* b_deg = nullptr;
+    long long* u_w = nullptr;    // Q24.40 1/ln(deg), 0 where deg <= 1
+    long long* b_w = nullptr;
+    blp_score_stats_t stats[2] = {};
+};
+
+namespace blp {
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+}  // namespace blp
+
+#define BLP_CUDA_TRY(expr)                                                     \
+    do {                                                                       \
+        cudaError_t e__ = (expr);                                              \
+        if (e__ != cudaSuccess) return blp::cuda_fail(e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#endif  // BLP_INTERNAL_H_

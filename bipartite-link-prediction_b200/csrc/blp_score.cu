@@ -1,0 +1,531 @@
+// Candidate-pair scoring kernels (sm_100a).
+//
+// One "side" of the reference's similarity.py is: build hop2(x) for every distinct grouping node
+// x (users() loop A, similarity.py:24-33 / business() loop A', :67-78), then for every candidate
+// pair (x, y) intersect hop2(x) with N(y) (loops C / C', :48-61 / :91-106) and derive
+// common_neighbors, jaccard and adamic_adar (:108-126).  Both sides are the same computation
+// with the two CSR directions swapped, so there is one kernel:
+//
+//   hop2(x) = ( U_{m in N(x)} N(m) ) \ {x}        held as a bitmap in shared memory
+//   cn(x,y) = | { i in N(y) : bit i set } |        N(y) streamed with 128-bit loads
+//
+// Work distribution.  Pairs are grouped by x with a counting sort (k_group_*).  A persistent grid
+// pulls groups from an atomic counter.  Inside a CTA both the expansion and the intersection
+// phase walk a *set of adjacency lists* whose lengths span 1 .. >100k: the lists of a tile are
+// cut into 512-id chunks, the chunk counts are prefix-summed in shared memory and warps take
+// chunks round-robin, so a hub list is spread over the whole CTA while short lists cost one
+// warp pass each (degree-bucketed scheduling without separate launches).
+#include <climits>
+#include <cstdio>
+
+#include "blp_internal.h"
+
+namespace blp {
+
+constexpr int kTile = 256;        // adjacency lists per scheduling tile
+constexpr int kChunkV4 = 128;     // int4 loads per chunk (4 per lane): 512 ids
+constexpr unsigned kFull = 0xffffffffu;
+
+struct SideArgs {
+    // grouping side x: rows x -> middle nodes m;   middle side: rows m -> nodes of x's side
+    const long long* __restrict__ g_off;
+    const int* __restrict__ g_adj;
+    const long long* __restrict__ m_off;
+    const int* __restrict__ m_adj;
+    const int* __restrict__ g_deg;
+    const int* __restrict__ m_deg;
+    const long long* __restrict__ g_w;   // Q24.40 weights of x-side nodes
+    int n_side;                           // number of x-side nodes == sentinel id of m rows
+    int bm_words;                         // bitmap words (covers bit n_side as well)
+    // grouping
+    const long long* __restrict__ grp_off;  // [n_side + 2]; key n_side = "not in graph"
+    const int* __restrict__ item_key;       // non-empty group keys
+    const int* __restrict__ n_items;
+    const int* __restrict__ perm;           // pair indices ordered by group
+    const int* __restrict__ partner;        // y of every pair, caller order
+    int* work_counter;
+    // outputs, caller order (any may be null)
+    int* cn;
+    int* uni;
+    double* jac;
+    double* aa;
+    long long* pa;
+    int* hop2;
+};
+
+__device__ __forceinline__ int4 ldg_stream(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grouping: counting sort of pair indices by the node whose hop-2 set they need.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int group_key(int x, int y, int n_side, int n_mid,
+                                         const int* __restrict__ g_deg,
+                                         const int* __restrict__ m_deg) {
+    bool ok = x >= 0 && x < n_side && y >= 0 && y < n_mid;
+    if (ok) ok = (g_deg[x] > 0) && (m_deg[y] > 0);
+    return ok ? x : n_side;   // similarity.py:52,59-60: any id not in the graph -> literal 0
+}
+
+__global__ void k_group_count(const int* __restrict__ gx, const int* __restrict__ gy, long long n,
+                              int n_side, int n_mid, const int* __restrict__ g_deg,
+                              const int* __restrict__ m_deg, unsigned* __restrict__ cnt) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int key = group_key(gx[i], gy[i], n_side, n_mid, g_deg, m_deg);
+        atomicAdd(&cnt[key], 1u);
+    }
+}
+
+// Single-CTA exclusive scan of the group sizes; also compacts the non-empty keys.
+__global__ void __launch_bounds__(1024) k_group_scan(const unsigned* __restrict__ cnt, int n_keys,
+                                                     long long* __restrict__ grp_off,
+                                                     unsigned* __restrict__ cursor,
+                                                     int* __restrict__ item_key,
+                                                     int* __restrict__ n_items) {
+    __shared__ long long s_sum[32];
+    __shared__ int s_flag[32];
+    __shared__ long long s_base;
+    __shared__ int s_fbase;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_base = 0;
+        s_fbase = 0;
+    }
+    __syncthreads();
+    for (int start = 0; start < n_keys; start += 1024) {
+        int i = start + tid;
+        unsigned c = i < n_keys ? cnt[i] : 0u;
+        long long v = c;
+        int f = c > 0;
+        // inclusive warp scans
+        for (int d = 1; d < 32; d <<= 1) {
+            long long t = __shfl_up_sync(kFull, v, d);
+            int tf = __shfl_up_sync(kFull, f, d);
+            if (lane >= d) {
+                v += t;
+                f += tf;
+            }
+        }
+        if (lane == 31) {
+            s_sum[warp] = v;
+            s_flag[warp] = f;
+        }
+        __syncthreads();
+        long long wb = 0;
+        int fb = 0;
+        for (int w = 0; w < warp; ++w) {
+            wb += s_sum[w];
+            fb += s_flag[w];
+        }
+        long long base = s_base;
+        int fbase = s_fbase;
+        if (i < n_keys) {
+            grp_off[i] = base + wb + v - c;
+            cursor[i] = 0u;
+            if (c > 0) item_key[fbase + fb + f - 1] = i;
+        }
+        __syncthreads();
+        if (tid == 1023) {
+            s_base = base + wb + v;
+            s_fbase = fbase + fb + f;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        grp_off[n_keys] = s_base;
+        *n_items = s_fbase;
+    }
+}
+
+__global__ void k_group_scatter(const int* __restrict__ gx, const int* __restrict__ gy,
+                                long long n, int n_side, int n_mid,
+                                const int* __restrict__ g_deg, const int* __restrict__ m_deg,
+                                const long long* __restrict__ grp_off,
+                                unsigned* __restrict__ cursor, int* __restrict__ perm) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int key = group_key(gx[i], gy[i], n_side, n_mid, g_deg, m_deg);
+        unsigned pos = atomicAdd(&cursor[key], 1u);
+        perm[grp_off[key] + pos] = (int)i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The scoring kernel.
+// ---------------------------------------------------------------------------------------------
+struct TileSmem {
+    long long start[kTile];            // first padded entry of the list
+    unsigned long long aa[kTile];      // Q24.40 Adamic-Adar accumulators
+    int n4[kTile];                     // list length in int4 units
+    int scan[kTile + 8];               // exclusive prefix of chunk counts, [kTile] = total
+    int cn[kTile];
+    int idx[kTile];                    // caller-order pair index
+    int pdeg[kTile];                   // true degree of the partner
+    int wsum[32];
+    int red[32];
+    int item;
+    int hop2;
+};
+
+// Exclusive scan of `v` over the first kTile threads into ts.scan[]; ts.scan[kTile] = total.
+template <int NT>
+__device__ __forceinline__ void tile_scan(TileSmem& ts, int v, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    int inc = v;
+    if (tid < kTile) {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(kFull, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) ts.wsum[warp] = inc;
+    }
+    __syncthreads();
+    if (tid < kTile) {
+        int base = 0;
+        for (int w = 0; w < warp; ++w) base += ts.wsum[w];
+        ts.scan[tid] = base + inc - v;
+        if (tid == kTile - 1) ts.scan[kTile] = base + inc;
+    }
+    __syncthreads();
+}
+
+// Which list owns chunk c?  Two 32-wide probes of the 257-entry prefix array (warp-uniform c).
+__device__ __forceinline__ int find_list(const TileSmem& ts, int c, int lane) {
+    int v = ts.scan[lane * 8];
+    int kb = __popc(__ballot_sync(kFull, v <= c)) - 1;
+    int v2 = lane < 8 ? ts.scan[kb * 8 + lane] : INT_MAX;
+    return kb * 8 + __popc(__ballot_sync(kFull, v2 <= c)) - 1;
+}
+
+__device__ __forceinline__ void set_bit(unsigned* bm, int id) {
+    unsigned bit = 1u << (id & 31);
+    unsigned* w = bm + (id >> 5);
+    // bits are only ever set during expansion, so a stale read can only cause a redundant atomic
+    if (!(*(volatile unsigned*)w & bit)) atomicOr(w, bit);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* bm = reinterpret_cast<unsigned*>(smem_raw);
+    TileSmem& ts = *reinterpret_cast<TileSmem*>(smem_raw + (size_t)a.bm_words * 4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    const int n_items = *a.n_items;
+    const int4 sent4 = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
+
+    for (;;) {
+        __syncthreads();   // previous item fully retired (ts.item, bitmap, tile arrays)
+        if (tid == 0) ts.item = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const int item = ts.item;
+        if (item >= n_items) break;
+        const int x = a.item_key[item];
+        const long long p0 = a.grp_off[x], p1 = a.grp_off[x + 1];
+
+        if (x >= a.n_side) {
+            // pairs with an id that is not in the graph: every score is the literal 0
+            for (long long k = p0 + tid; k < p1; k += NT) {
+                int idx = a.perm[k];
+                if (a.cn) a.cn[idx] = 0;
+                if (a.uni) a.uni[idx] = 0;
+                if (a.jac) a.jac[idx] = 0.0;
+                if (a.aa) a.aa[idx] = 0.0;
+                if (a.pa) a.pa[idx] = 0;
+                if (a.hop2) a.hop2[idx] = 0;
+            }
+            continue;
+        }
+
+        // ---- phase 0: clear the bitmap
+        {
+            uint4* b4 = reinterpret_cast<uint4*>(bm);
+            const int n4 = a.bm_words >> 2;   // bm_words is a multiple of 4
+            for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        const int xdeg = a.g_deg[x];
+        const long long xrow = a.g_off[x];
+        __syncthreads();
+
+        // ---- phase 1: two-hop expansion, hop2(x) |= N(m) for every m in N(x)
+        for (int tb = 0; tb < xdeg; tb += kTile) {
+            int nch = 0;
+            if (tid < kTile) {
+                int li = tb + tid;
+                if (li < xdeg) {
+                    int m = a.g_adj[xrow + li];
+                    long long s = a.m_off[m], e = a.m_off[m + 1];
+                    int n4 = (int)((e - s) >> 2);
+                    ts.start[tid] = s;
+                    ts.n4[tid] = n4;
+                    nch = (n4 + kChunkV4 - 1) / kChunkV4;
+                }
+            }
+            tile_scan<NT>(ts, nch, tid);
+            const int total = ts.scan[kTile];
+            for (int c = warp; c < total; c += NW) {
+                int j = find_list(ts, c, lane);
+                int off4 = (c - ts.scan[j]) * kChunkV4;
+                int n = min(kChunkV4, ts.n4[j] - off4);
+                const int4* p = reinterpret_cast<const int4*>(a.m_adj + ts.start[j]) + off4;
+                int4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int i = lane + 32 * k;
+                    v[k] = i < n ? ldg_stream(p + i) : sent4;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    set_bit(bm, v[k].x);
+                    set_bit(bm, v[k].y);
+                    set_bit(bm, v[k].z);
+                    set_bit(bm, v[k].w);
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- phase 2: |hop2(x)| = popcount minus x itself and the padding sentinel
+        {
+            int c = 0;
+            for (int i = tid; i < a.bm_words; i += NT) c += __popc(bm[i]);
+            c = __reduce_add_sync(kFull, c);
+            int adj = 0;
+            if (tid == 0) {
+                adj = ((bm[x >> 5] >> (x & 31)) & 1) + ((bm[a.n_side >> 5] >> (a.n_side & 31)) & 1);
+            }
+            if (lane == 0) ts.red[warp] = c;
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int w = 0; w < NW; ++w) tot += ts.red[w];
+                ts.hop2 = tot - adj;
+                bm[x >> 5] &= ~(1u << (x & 31));
+                bm[a.n_side >> 5] &= ~(1u << (a.n_side & 31));
+            }
+            __syncthreads();
+        }
+        const int hop2 = ts.hop2;
+
+        // ---- phase 3: every pair (x, y) of the group: stream N(y), test, count, weigh
+        for (long long tb = p0; tb < p1; tb += kTile) {
+            int nch = 0;
+            if (tid < kTile) {
+                long long k = tb + tid;
+                if (k < p1) {
+                    int idx = a.perm[k];
+                    int y = a.partner[idx];
+                    long long s = a.m_off[y], e = a.m_off[y + 1];
+                    int n4 = (int)((e - s) >> 2);
+                    ts.start[tid] = s;
+                    ts.n4[tid] = n4;
+                    ts.idx[tid] = idx;
+                    ts.pdeg[tid] = a.m_deg[y];
+                    ts.cn[tid] = 0;
+                    ts.aa[tid] = 0ull;
+                    nch = (n4 + kChunkV4 - 1) / kChunkV4;
+                }
+            }
+            tile_scan<NT>(ts, nch, tid);
+            const int total = ts.scan[kTile];
+            for (int c = warp; c < total; c += NW) {
+                int j = find_list(ts, c, lane);
+                int off4 = (c - ts.scan[j]) * kChunkV4;
+                int n = min(kChunkV4, ts.n4[j] - off4);
+                const int4* p = reinterpret_cast<const int4*>(a.m_adj + ts.start[j]) + off4;
+                int4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int i = lane + 32 * k;
+                    v[k] = i < n ? ldg_stream(p + i) : sent4;
+                }
+                int cnt = 0;
+                unsigned long long acc = 0ull;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ids[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int id = ids[q];
+                        if ((bm[id >> 5] >> (id & 31)) & 1u) {
+                            ++cnt;
+                            acc += (unsigned long long)__ldg(a.g_w + id);
+                        }
+                    }
+                }
+                if (__any_sync(kFull, cnt > 0)) {
+                    cnt = __reduce_add_sync(kFull, cnt);
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
+                    if (lane == 0) {
+                        atomicAdd(&ts.cn[j], cnt);
+                        atomicAdd(&ts.aa[j], acc);
+                    }
+                }
+            }
+            __syncthreads();
+            // epilogue: one thread per pair of the tile
+            if (tid < kTile && tb + tid < p1) {
+                int idx = ts.idx[tid];
+                int c = ts.cn[tid];
+                int pdeg = ts.pdeg[tid];
+                int u = hop2 + pdeg - c;   // |a| + |b| - |a & b|  (similarity.py:110)
+                if (a.cn) a.cn[idx] = c;
+                if (a.uni) a.uni[idx] = u;
+                if (a.jac) a.jac[idx] = __ddiv_rn((double)c, (double)u);
+                if (a.aa) a.aa[idx] = (double)ts.aa[tid] * (1.0 / (double)(1ull << BLP_AA_FRAC_BITS));
+                if (a.pa) a.pa[idx] = (long long)xdeg * (long long)pdeg;
+                if (a.hop2) a.hop2[idx] = hop2;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int NT>
+static int launch_side(const SideArgs& a, int grid, size_t smem, cudaStream_t st) {
+    BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_side<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    k_score_side<NT><<<grid, NT, smem, st>>>(a);
+    BLP_CUDA_TRY(cudaGetLastError());
+    return BLP_OK;
+}
+
+template <int NT>
+static int occupancy(size_t smem, int* ctas_per_sm) {
+    BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_side<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    BLP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_score_side<NT>, NT, smem));
+    return BLP_OK;
+}
+
+}  // namespace blp
+
+extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, const int32_t* pair_b,
+                               int64_t n, int32_t* cn, int32_t* uni, double* jaccard,
+                               double* adamic, int64_t* pa, int32_t* hop2_size, void* stream) {
+    using namespace blp;
+    if (!g || (side != BLP_SIDE_USER && side != BLP_SIDE_BUSINESS) || n < 0 ||
+        (n > 0 && (!pair_u || !pair_b))) {
+        set_error("blp_score_pairs: bad argument");
+        return BLP_ERR_INVALID;
+    }
+    if (n >= (int64_t)INT_MAX) {
+        set_error("blp_score_pairs: at most 2^31-2 pairs per call; split the pair list");
+        return BLP_ERR_UNSUPPORTED;
+    }
+    BLP_CUDA_TRY(cudaSetDevice(g->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    blp_score_stats_t& stats = g->stats[side];
+    stats = blp_score_stats_t{};
+    stats.n_pairs = n;
+    if (n == 0) return BLP_OK;
+
+    const bool us = side == BLP_SIDE_USER;
+    SideArgs a{};
+    a.g_off = us ? g->u_off : g->b_off;
+    a.g_adj = us ? g->u_adj : g->b_adj;
+    a.m_off = us ? g->b_off : g->u_off;
+    a.m_adj = us ? g->b_adj : g->u_adj;
+    a.g_deg = us ? g->u_deg : g->b_deg;
+    a.m_deg = us ? g->b_deg : g->u_deg;
+    a.g_w = us ? g->u_w : g->b_w;
+    a.n_side = us ? g->n_users : g->n_biz;
+    const int n_mid = us ? g->n_biz : g->n_users;
+    const int* gx = us ? pair_u : pair_b;
+    const int* gy = us ? pair_b : pair_u;
+    a.partner = gy;
+    a.cn = cn;
+    a.uni = uni;
+    a.jac = jaccard;
+    a.aa = adamic;
+    a.pa = (long long*)pa;
+    a.hop2 = hop2_size;
+
+    // bitmap must hold bits 0..n_side (the last one is the padding sentinel), 16-byte multiple
+    a.bm_words = (int)((((long long)a.n_side + 1 + 31) / 32 + 3) & ~3LL);
+    const size_t smem = (size_t)a.bm_words * 4 + sizeof(TileSmem);
+    if (smem > (size_t)g->max_smem_optin) {
+        char buf[200];
+        snprintf(buf, sizeof(buf),
+                 "blp_score_pairs: hop-2 bitmap of %d nodes needs %zu B of shared memory, device "
+                 "offers %d B per CTA (id-range passes not built yet)",
+                 a.n_side, smem, g->max_smem_optin);
+        set_error(buf);
+        return BLP_ERR_UNSUPPORTED;
+    }
+
+    // ---- stream-ordered scratch
+    const int n_keys = a.n_side + 1;
+    unsigned *cnt = nullptr, *cursor = nullptr;
+    long long* grp_off = nullptr;
+    int *item_key = nullptr, *perm = nullptr, *scalars = nullptr;
+    BLP_CUDA_TRY(cudaMallocAsync((void**)&cnt, sizeof(unsigned) * (size_t)n_keys, st));
+    BLP_CUDA_TRY(cudaMallocAsync((void**)&cursor, sizeof(unsigned) * (size_t)n_keys, st));
+    BLP_CUDA_TRY(cudaMallocAsync((void**)&grp_off, sizeof(long long) * ((size_t)n_keys + 1), st));
+    BLP_CUDA_TRY(cudaMallocAsync((void**)&item_key, sizeof(int) * (size_t)n_keys, st));
+    BLP_CUDA_TRY(cudaMallocAsync((void**)&perm, sizeof(int) * (size_t)n, st));
+    BLP_CUDA_TRY(cudaMallocAsync((void**)&scalars, sizeof(int) * 2, st));
+    BLP_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
+    BLP_CUDA_TRY(cudaMemsetAsync(scalars, 0, sizeof(int) * 2, st));
+
+    const int gblocks = (int)std::min<long long>((n + 255) / 256, (long long)g->sm_count * 16);
+    k_group_count<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, a.g_deg, a.m_deg, cnt);
+    BLP_CUDA_TRY(cudaGetLastError());
+    k_group_scan<<<1, 1024, 0, st>>>(cnt, n_keys, grp_off, cursor, item_key, scalars);
+    BLP_CUDA_TRY(cudaGetLastError());
+    k_group_scatter<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, a.g_deg, a.m_deg, grp_off,
+                                             cursor, perm);
+    BLP_CUDA_TRY(cudaGetLastError());
+
+    a.grp_off = grp_off;
+    a.item_key = item_key;
+    a.n_items = scalars;
+    a.work_counter = scalars + 1;
+    a.perm = perm;
+
+    // ---- persistent scoring grid: as many CTAs per SM as the bitmap allows
+    int per_sm = 0, nt = 0, rc = BLP_OK;
+    const size_t budget = (size_t)g->max_smem_optin;
+    if (smem * 4 + 4096 <= budget) {
+        nt = 256;
+        rc = occupancy<256>(smem, &per_sm);
+    } else if (smem * 2 + 2048 <= budget) {
+        nt = 512;
+        rc = occupancy<512>(smem, &per_sm);
+    } else {
+        nt = 1024;
+        rc = occupancy<1024>(smem, &per_sm);
+    }
+    if (rc == BLP_OK && per_sm < 1) {
+        set_error("blp_score_pairs: scoring kernel does not fit on an SM");
+        rc = BLP_ERR_UNSUPPORTED;
+    }
+    if (rc == BLP_OK) {
+        const int grid = per_sm * g->sm_count;
+        if (nt == 256) rc = launch_side<256>(a, grid, smem, st);
+        else if (nt == 512) rc = launch_side<512>(a, grid, smem, st);
+        else rc = launch_side<1024>(a, grid, smem, st);
+        stats.ctas = grid;
+        stats.threads_per_cta = nt;
+        stats.smem_bytes = (int)smem;
+        stats.kernel_launches = 4;
+        stats.range_passes = 1;
+    }
+    cudaFreeAsync(cnt, st);
+    cudaFreeAsync(cursor, st);
+    cudaFreeAsync(grp_off, st);
+    cudaFreeAsync(item_key, st);
+    cudaFreeAsync(perm, st);
+    cudaFreeAsync(scalars, st);
+    return rc;
+}

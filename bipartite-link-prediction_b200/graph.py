@@ -1,0 +1,263 @@
+"""Graph handle: the object that stands where the reference passes a SNAP ``PUNGraph``.
+
+The reference loads ``graph.txt`` with ``snap.LoadEdgeList(snap.PUNGraph, f, 0, 1)``
+(similarity.py:16) and then only ever asks the graph for its node ids (:22,:65), BFS hops
+(:29,:41,:74,:85) and degrees (:121).  ``BipartiteGraph`` owns the device-resident CSR pair behind
+the C ABI (include/blp.h) and offers those SNAP spellings for the set-level helpers; the bulk
+scoring goes through ``score_pairs`` -> ``blp_score_pairs`` (CUDA, no CPU path).
+
+PyTorch is used here for device buffers and streams only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+OUTPUTS_PER_SIDE = ('cn', 'union', 'jaccard', 'adamic')
+
+
+def read_edge_list(path):
+    """graph.txt -> two int64 arrays (column 0 = user id, column 1 = business id).
+
+    Format: one ``"<user_id> <business_id>\\n"`` per review, duplicates allowed
+    (dataset_maker.py:197).
+    """
+    try:
+        import pandas as pd
+        df = pd.read_csv(path, sep=r'\s+', header=None, usecols=[0, 1], dtype=np.int64,
+                         engine='c')
+        return df[0].to_numpy(), df[1].to_numpy()
+    except ImportError:  # pragma: no cover
+        arr = np.loadtxt(path, dtype=np.int64, usecols=(0, 1), ndmin=2)
+        return arr[:, 0].copy(), arr[:, 1].copy()
+
+
+class _NodeIt(object):
+    """``G.GetNI(i)`` -- only ``GetDeg`` / ``GetId`` are used by the reference (similarity.py:22,121)."""
+
+    def __init__(self, nid, deg):
+        self._nid, self._deg = nid, deg
+
+    def GetDeg(self):
+        return self._deg
+
+    def GetId(self):
+        return self._nid
+
+
+class BipartiteGraph(object):
+    """De-duplicated user x business graph, resident in HBM on one device.
+
+    Two ways in:
+      * ``BipartiteGraph(n_users, n_biz, edge_u, edge_b)`` -- LOCAL indices (users 0..n_users-1,
+        businesses 0..n_biz-1); nodes that appear on no edge have degree 0 = "not in graph".
+      * ``BipartiteGraph.from_id_edges(ids_u, ids_b)`` / ``from_edge_list(path)`` -- the
+        reference's shared id space; ids are compacted, and the two columns must be disjoint
+        (dataset_maker.py:173-174 guarantees it; hop-2 means something else otherwise).
+    """
+
+    def __init__(self, n_users, n_biz, edge_u, edge_b, device=None, user_ids=None, biz_ids=None):
+        lib = _lib.load()
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        if isinstance(device, torch.device):
+            device = device.index or 0
+        eu = np.ascontiguousarray(np.asarray(edge_u), dtype=np.int32)
+        eb = np.ascontiguousarray(np.asarray(edge_b), dtype=np.int32)
+        if eu.shape != eb.shape or eu.ndim != 1:
+            raise ValueError('edge_u and edge_b must be 1-D arrays of equal length')
+        self._lib = lib
+        self._h = ctypes.c_void_p()
+        rc = lib.blp_graph_create(int(n_users), int(n_biz), int(eu.size),
+                                  eu.ctypes.data_as(ctypes.c_void_p),
+                                  eb.ctypes.data_as(ctypes.c_void_p), int(device),
+                                  ctypes.byref(self._h))
+        _lib.check(rc, 'blp_graph_create')
+        self.device = torch.device('cuda', int(device))
+        self.n_users, self.n_biz = int(n_users), int(n_biz)
+        # shared-id-space view (sorted id tables), None when built from local indices
+        self.user_ids = None if user_ids is None else np.asarray(user_ids, dtype=np.int64)
+        self.biz_ids = None if biz_ids is None else np.asarray(biz_ids, dtype=np.int64)
+        self._deg = [None, None]
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_id_edges(cls, ids_u, ids_b, device=None):
+        ids_u = np.asarray(ids_u, dtype=np.int64)
+        ids_b = np.asarray(ids_b, dtype=np.int64)
+        users, eu = np.unique(ids_u, return_inverse=True)
+        bizs, eb = np.unique(ids_b, return_inverse=True)
+        if users.size == 0:
+            raise ValueError('empty edge list')
+        if np.intersect1d(users, bizs, assume_unique=True).size:
+            raise ValueError('graph is not bipartite by column: some id appears both as a user '
+                             '(column 0) and as a business (column 1)')
+        return cls(users.size, bizs.size, eu, eb, device=device, user_ids=users, biz_ids=bizs)
+
+    @classmethod
+    def from_edge_list(cls, path, src_col=0, dst_col=1, device=None):
+        if (src_col, dst_col) != (0, 1):
+            raise ValueError('column 0 must hold users and column 1 businesses')
+        u, b = read_edge_list(path)
+        return cls.from_id_edges(u, b, device=device)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            self._lib.blp_graph_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ introspection
+    def info(self):
+        gi = _lib.GraphInfo()
+        _lib.check(self._lib.blp_graph_info(self._h, ctypes.byref(gi)), 'blp_graph_info')
+        return gi.as_dict()
+
+    def degrees(self, side):
+        """De-duplicated degrees of one side as a host int32 array (cached)."""
+        if self._deg[side] is None:
+            n = self.n_users if side == _lib.SIDE_USER else self.n_biz
+            out = np.empty(n, dtype=np.int32)
+            _lib.check(self._lib.blp_graph_degrees(self._h, side,
+                                                   out.ctypes.data_as(ctypes.c_void_p)),
+                       'blp_graph_degrees')
+            self._deg[side] = out
+        return self._deg[side]
+
+    # ------------------------------------------------------------------ id space
+    @staticmethod
+    def _lookup(table, ids):
+        ids = np.asarray(ids, dtype=np.int64)
+        pos = np.searchsorted(table, ids)
+        pos[pos >= table.size] = 0
+        hit = table[pos] == ids
+        return np.where(hit, pos, -1).astype(np.int32)
+
+    def local_users(self, ids):
+        """Shared-space ids -> local user indices, -1 where the id is not a user of the graph."""
+        if self.user_ids is None:
+            ids = np.asarray(ids, dtype=np.int64)
+            return np.where((ids >= 0) & (ids < self.n_users), ids, -1).astype(np.int32)
+        return self._lookup(self.user_ids, ids)
+
+    def local_businesses(self, ids):
+        if self.biz_ids is None:
+            ids = np.asarray(ids, dtype=np.int64)
+            return np.where((ids >= 0) & (ids < self.n_biz), ids, -1).astype(np.int32)
+        return self._lookup(self.biz_ids, ids)
+
+    # SNAP spellings used by the reference's set-level helpers ---------------------------
+    def GetNI(self, nid):
+        """``G.GetNI(i).GetDeg()`` (similarity.py:121) for an id of the shared id space."""
+        u = int(self.local_users([nid])[0])
+        if u >= 0 and self.degrees(_lib.SIDE_USER)[u] > 0:
+            return _NodeIt(nid, int(self.degrees(_lib.SIDE_USER)[u]))
+        b = int(self.local_businesses([nid])[0])
+        if b >= 0 and self.degrees(_lib.SIDE_BUSINESS)[b] > 0:
+            return _NodeIt(nid, int(self.degrees(_lib.SIDE_BUSINESS)[b]))
+        raise RuntimeError('node %r is not in the graph' % (nid,))
+
+    def Nodes(self):
+        """``snap.Nodes(G)``: node iterators of every id with degree >= 1 (similarity.py:22)."""
+        du, db = self.degrees(_lib.SIDE_USER), self.degrees(_lib.SIDE_BUSINESS)
+        uid = self.user_ids if self.user_ids is not None else np.arange(self.n_users)
+        bid = self.biz_ids if self.biz_ids is not None else np.arange(self.n_biz)
+        for i in np.nonzero(du > 0)[0]:
+            yield _NodeIt(int(uid[i]), int(du[i]))
+        for i in np.nonzero(db > 0)[0]:
+            yield _NodeIt(int(bid[i]), int(db[i]))
+
+    def GetNodes(self):
+        i = self.info()
+        return i['n_users_in_graph'] + i['n_biz_in_graph']
+
+    def GetEdges(self):
+        return self.info()['n_edges']
+
+    # ------------------------------------------------------------------ scoring
+    def score_side(self, side, pair_u, pair_b, want=OUTPUTS_PER_SIDE, want_pa=False,
+                   want_hop2=False, out=None, stream=None):
+        """One ``blp_score_pairs`` call.  pair_u / pair_b: int32 CUDA tensors of local indices.
+
+        Returns a dict of CUDA tensors (keys from ``want`` plus 'pa' / 'hop2' when asked).
+        ``out`` may carry preallocated tensors under the same keys.
+        """
+        if not (pair_u.is_cuda and pair_b.is_cuda):
+            raise ValueError('pair_u / pair_b must be CUDA tensors (use score_pairs_host for '
+                             'host arrays)')
+        if pair_u.dtype != torch.int32 or pair_b.dtype != torch.int32:
+            raise ValueError('pair_u / pair_b must be int32')
+        if pair_u.device != self.device or pair_b.device != self.device:
+            raise ValueError('pairs live on %s, graph on %s' % (pair_u.device, self.device))
+        pair_u, pair_b = pair_u.contiguous(), pair_b.contiguous()
+        n = pair_u.numel()
+        if pair_b.numel() != n:
+            raise ValueError('pair_u and pair_b differ in length')
+        dtypes = {'cn': torch.int32, 'union': torch.int32, 'jaccard': torch.float64,
+                  'adamic': torch.float64, 'pa': torch.int64, 'hop2': torch.int32}
+        keys = list(want) + (['pa'] if want_pa else []) + (['hop2'] if want_hop2 else [])
+        res = {}
+        for k in keys:
+            t = None if out is None else out.get(k)
+            if t is None:
+                t = torch.empty(n, dtype=dtypes[k], device=self.device)
+            elif t.dtype != dtypes[k] or t.numel() != n or not t.is_contiguous():
+                raise ValueError('preallocated output %r has the wrong dtype/size' % k)
+            res[k] = t
+
+        def ptr(k):
+            return ctypes.c_void_p(res[k].data_ptr()) if k in res else None
+
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        rc = self._lib.blp_score_pairs(self._h, int(side), ctypes.c_void_p(pair_u.data_ptr()),
+                                       ctypes.c_void_p(pair_b.data_ptr()), n, ptr('cn'),
+                                       ptr('union'), ptr('jaccard'), ptr('adamic'), ptr('pa'),
+                                       ptr('hop2'), ctypes.c_void_p(stream.cuda_stream))
+        _lib.check(rc, 'blp_score_pairs')
+        return res
+
+    def score_pairs(self, pair_u, pair_b, want_hop2=False, out=None, stream=None):
+        """All seven reference outputs of every pair: u_cn,u_jaccard,u_adamic,b_cn,b_jaccard,
+        b_adamic,pa (plus the two union sizes).  Device tensors in, device tensors out."""
+        o_u = None if out is None else {k[2:]: v for k, v in out.items() if k.startswith('u_')}
+        o_b = None if out is None else {k[2:]: v for k, v in out.items() if k.startswith('b_')}
+        if out is not None and 'pa' in out:
+            o_u['pa'] = out['pa']
+        ru = self.score_side(_lib.SIDE_USER, pair_u, pair_b, want_pa=True, want_hop2=want_hop2,
+                             out=o_u, stream=stream)
+        rb = self.score_side(_lib.SIDE_BUSINESS, pair_u, pair_b, want_hop2=want_hop2, out=o_b,
+                             stream=stream)
+        res = {'u_' + k: v for k, v in ru.items() if k != 'pa'}
+        res.update({'b_' + k: v for k, v in rb.items()})
+        res['pa'] = ru['pa']
+        return res
+
+    def score_stats(self, side):
+        st = _lib.ScoreStats()
+        _lib.check(self._lib.blp_score_stats(self._h, side, ctypes.byref(st)), 'blp_score_stats')
+        return st.as_dict()
+
+    def score_pairs_host(self, pair_u, pair_b, want_hop2=False):
+        """Host arrays of LOCAL indices in, dict of host numpy arrays out (H2D + score + D2H)."""
+        pu = torch.from_numpy(np.ascontiguousarray(pair_u, dtype=np.int32))
+        pv = torch.from_numpy(np.ascontiguousarray(pair_b, dtype=np.int32))
+        with torch.cuda.device(self.device):
+            du = pu.to(self.device, non_blocking=False)
+            dv = pv.to(self.device, non_blocking=False)
+            res = self.score_pairs(du, dv, want_hop2=want_hop2)
+            host = {k: v.cpu().numpy() for k, v in res.items()}
+        return host
+
+    def score_id_pairs(self, ids_u, ids_b, want_hop2=False):
+        """Same, for ids of the reference's shared id space (unknown ids score 0)."""
+        return self.score_pairs_host(self.local_users(ids_u), self.local_businesses(ids_b),
+                                     want_hop2=want_hop2)

@@ -1,0 +1,128 @@
+/*
+ * blp.h -- C ABI of the B200-native candidate-pair similarity scorer.
+ *
+ * This is the drop-in boundary for ONE path of es1985/bipartite-link-prediction: the
+ * neighbourhood similarity scores of similarity.py.  The reference has no FFI of its own for this
+ * path -- it crosses Python->SWIG->C++ (SNAP) four times and does the set arithmetic in Python --
+ * so each entry point below names the reference call sites it replaces (file:line relative to
+ * the reference checkout).  INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - Every function returns an int: BLP_OK (0) or a negative blp_status.  Nothing throws across
+ *     the boundary and nothing calls exit().  blp_last_error() returns a thread-local message.
+ *   - The caller owns every buffer.  The library owns only the graph handle (CSR arrays, degree
+ *     and weight tables in HBM) and stream-ordered scratch it allocates and frees per call.
+ *   - Indices are LOCAL: users 0..n_users-1, businesses 0..n_biz-1 (the host layer maps the
+ *     reference's shared id space onto them).  In a pair, an index that is negative, out of range
+ *     or names a node of degree 0 means "id not in graph": every output of that pair is 0
+ *     (similarity.py:59-60, 104-105).
+ *   - A handle is immutable after creation; scoring calls on distinct streams are re-entrant.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     BLP_ERR_CUDA.
+ */
+#ifndef BLP_H_
+#define BLP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLP_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum blp_status {
+    BLP_OK = 0,
+    BLP_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, bad side, ...) */
+    BLP_ERR_CUDA = -2,        /* CUDA runtime / driver error, or no device */
+    BLP_ERR_OOM = -3,         /* host or device allocation failed */
+    BLP_ERR_RANGE = -4,       /* an edge endpoint is outside [0,n_users) x [0,n_biz) */
+    BLP_ERR_UNSUPPORTED = -5  /* configuration outside what this build handles */
+} blp_status;
+
+typedef enum blp_side {
+    BLP_SIDE_USER = 0,     /* hop-2 set of the user, neighbours of the business (similarity.py:20-61) */
+    BLP_SIDE_BUSINESS = 1  /* hop-2 set of the business, neighbours of the user (similarity.py:63-106) */
+} blp_side;
+
+typedef struct blp_graph blp_graph; /* opaque; one per device / rank */
+
+typedef struct blp_graph_info_t {
+    int32_t n_users;
+    int32_t n_biz;
+    int64_t n_edges_in;       /* edge lines given */
+    int64_t n_edges;          /* distinct edges kept (duplicates collapse, as in SNAP's TUNGraph) */
+    int32_t n_users_in_graph; /* users with degree >= 1 */
+    int32_t n_biz_in_graph;
+    int32_t max_user_degree;
+    int32_t max_biz_degree;
+    int64_t device_bytes;     /* HBM held by the handle */
+    int32_t device;
+    int32_t sm_count;
+} blp_graph_info_t;
+
+/* Per-launch accounting of the last blp_score_pairs call on a handle (for bench / roofline). */
+typedef struct blp_score_stats_t {
+    int64_t n_pairs;
+    int64_t n_groups;         /* distinct hop-2 sets built */
+    int32_t kernel_launches;  /* kernels launched by the call */
+    int32_t ctas;             /* grid of the scoring kernel */
+    int32_t threads_per_cta;
+    int32_t smem_bytes;       /* dynamic shared memory per CTA */
+    int32_t range_passes;     /* id-range passes over the hop-2 bitmap (1 = fits shared memory) */
+} blp_score_stats_t;
+
+int blp_version(void);
+const char* blp_last_error(void);
+/* 0 when a CUDA device is usable, BLP_ERR_CUDA otherwise (never touches a device buffer). */
+int blp_device_count(int* count);
+
+/*
+ * Build the graph handle.  Replaces snap.LoadEdgeList(snap.PUNGraph, graph_file, 0, 1)
+ * (similarity.py:16) and the node-id list of similarity.py:22,65: duplicate edges collapse, both
+ * CSR directions, degree tables and the Adamic-Adar weight table 1/ln(deg) (similarity.py:121-123)
+ * are made resident in HBM.  edge_u / edge_b are HOST arrays of n_edges local indices
+ * (column 0 = user, column 1 = business of graph.txt, dataset_maker.py:197).
+ */
+int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
+                     const int32_t* edge_u, const int32_t* edge_b,
+                     int device, blp_graph** out);
+int blp_graph_destroy(blp_graph* g);
+int blp_graph_info(const blp_graph* g, blp_graph_info_t* info);
+
+/* De-duplicated degrees (G.GetNI(i).GetDeg(), similarity.py:121) copied to a HOST array of
+ * n_users (side USER) or n_biz (side BUSINESS) int32. */
+int blp_graph_degrees(const blp_graph* g, int side, int32_t* host_out);
+
+/*
+ * Score n candidate pairs from one side.  Replaces loops A/B/C of users() (similarity.py:24-61)
+ * for side USER and loops A'/B'/C' of business() (similarity.py:67-106) for side BUSINESS,
+ * together with common_neighbors / jaccard / adamic_adar (similarity.py:108-126) -- one pass
+ * produces what the reference computes with three separate intersections per pair.
+ *
+ * pair_u / pair_b and every output are DEVICE arrays of n elements in the caller's pair order
+ * (any order; the library groups pairs by the node whose hop-2 set they share).  Outputs:
+ *   cn        int32   |hop2(x) & N(y)|                      (similarity.py:113-114), bit-exact
+ *   uni       int32   |hop2(x) | N(y)|                      (similarity.py:110), bit-exact
+ *   jaccard   double  (double)cn / (double)uni, div.rn       (similarity.py:108-111), bit-exact
+ *   adamic    double  sum over matched i with deg(i)>1 of 1/ln(deg(i)) (similarity.py:116-126);
+ *                     accumulated in 2^-40 fixed point so the result does not depend on
+ *                     summation order, bucket or rank count (|err| <= cn*2^-41, rel <= 1e-11)
+ *   pa        int64   deg(u)*deg(v)  ("Link prediction.R":400-415); may be NULL
+ *   hop2_size int32   |hop2(x)| of the pair's grouping node; may be NULL (debug / tests)
+ * with x = user, y = business for side USER and x = business, y = user for side BUSINESS.
+ * cn, uni, jaccard, adamic may each be NULL to skip that output.
+ * `stream` is a cudaStream_t (NULL = legacy default stream).  The call is asynchronous.
+ */
+int blp_score_pairs(blp_graph* g, int side,
+                    const int32_t* pair_u, const int32_t* pair_b, int64_t n,
+                    int32_t* cn, int32_t* uni, double* jaccard, double* adamic,
+                    int64_t* pa, int32_t* hop2_size, void* stream);
+
+/* Accounting of the most recent blp_score_pairs on this handle (per side). */
+int blp_score_stats(const blp_graph* g, int side, blp_score_stats_t* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLP_H_ */
