@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- candidate pairs scored per second on Yelp-shaped synthetic inputs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl reference]
+
+A "step" is one pass of the hot path over one batch: every pair of the workload gets all seven
+reference outputs (u_cn,u_jaccard,u_adamic,b_cn,b_jaccard,b_adamic,pa, plus both union sizes).
+N=1 workload: BASELINE.json configs[1] ("C2": 366k users x 61k businesses, 1.5M reviews, 10M
+candidate pairs).  N>1: weak scaling -- the adjacency is replicated, every rank scores its own
+10M-pair shard of a 10M*N pair list, no collective inside the timed region; the final NCCL
+gather of the result records is timed separately and reported under "gather".
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput (CUDA events, max over
+ranks); `e2e` goes through the host-buffer API (pinned H2D of the pair ids, D2H of 56 B/pair);
+`roofline` is the user-side scoring kernel (the dominant one) against MEASURED_PEAKS.json;
+`cpu_baseline` is the reference's algorithm (oracle/similarity_oracle.py, a line-for-line
+Python 3 re-execution -- the reference's own Python-2 + `_snap.so` code cannot run) on the host
+cores over a bounded sample.  `--impl reference` prints that baseline as its own line.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = 'bipartite-link-prediction_b200'
+METRIC = 'candidate pairs scored/sec'
+UNIT = 'pairs/s'
+METHODS = ['common_neighbors', 'jaccard', 'adamic_adar']
+NOTE = ('reference _snap.so (Python 2) unavailable -- CPU baseline is a line-for-line '
+        "re-execution of similarity.py's formulas (oracle/similarity_oracle.py, set membership)")
+
+
+def pkg(sub):
+    return importlib.import_module(PKG + '.' + sub)
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+_G = None
+_EX = None
+
+
+def _cpu_worker(args):
+    side, keys = args
+    from oracle import similarity_oracle as oa
+    ex = {k: _EX[k] for k in keys}
+    t = time.perf_counter()
+    if side == 'u':
+        oa.users(ex, _G, METHODS, [None] * 3, write=False)
+    else:
+        oa.business(ex, _G, METHODS, [None] * 3, write=False)
+    return time.perf_counter() - t
+
+
+def cpu_reference(cfg, eu, eb, pu, pv, n_user_groups, n_biz_groups, procs):
+    """Times the reference algorithm on structure-preserving samples of the workload.
+
+    User side: ALL pairs of the first `n_user_groups` example users (hop2(u) amortised over the
+    same K pairs as in the full run).  Business side: ALL pairs of `n_biz_groups` seeded-random
+    candidate businesses (hop2(v) amortised over as many pairs as in the full run).  The two
+    per-pair costs add: rate = 1 / (t_u/S_u + t_b/S_b).  Graph loading is not timed.
+    """
+    global _G, _EX
+    import multiprocessing as mp
+    from oracle import similarity_oracle as oa
+    synth = pkg('synth')
+    n_users = cfg['n_users']
+    ok = (pu >= 0) & (pv >= 0)
+    ids_eu, ids_eb = synth.shared_ids(n_users, eu, eb)
+    _G = oa.MiniSnapGraph.from_edges(zip(ids_eu.tolist(), ids_eb.tolist()))
+    ctx = mp.get_context('fork')
+
+    def run(side, sel):
+        global _EX
+        ids_pu, ids_pv = synth.shared_ids(n_users, pu[sel], pv[sel])
+        _EX = synth.examples_dict(ids_pu, ids_pv)
+        keys = list(_EX.keys())
+        if side == 'b':
+            # shard by business so that every hop2(v) is built once, as in one process
+            byb = {}
+            for u in keys:
+                for v in _EX[u]:
+                    byb.setdefault(v, []).append(u)
+            bl = list(byb.keys())
+            shards = []
+            for p in range(procs):
+                us = set()
+                for v in bl[p::procs]:
+                    us.update(byb[v])
+                shards.append(sorted(us))
+            # each shard only keeps its own businesses' pairs
+            full = _EX
+            packs = []
+            for p in range(procs):
+                mine = set(bl[p::procs])
+                packs.append({u: {v: 0 for v in full[u] if v in mine} for u in shards[p]})
+            t0 = time.perf_counter()
+            with ctx.Pool(procs) as pool:
+                pool.map(_cpu_worker_packed, [('b', pk) for pk in packs])
+            return time.perf_counter() - t0, int(sel.sum())
+        shards = [keys[p::procs] for p in range(procs)]
+        t0 = time.perf_counter()
+        with ctx.Pool(procs) as pool:
+            pool.map(_cpu_worker, [(side, sh) for sh in shards])
+        return time.perf_counter() - t0, int(sel.sum())
+
+    users_sorted = np.unique(pu[ok])
+    sel_u = ok & np.isin(pu, users_sorted[:n_user_groups])
+    rng = np.random.default_rng(7)
+    bizs = np.unique(pv[ok])
+    sel_b = ok & np.isin(pv, rng.choice(bizs, size=min(n_biz_groups, bizs.size), replace=False))
+    t_u, s_u = run('u', sel_u)
+    t_b, s_b = run('b', sel_b)
+    rate = 1.0 / (t_u / s_u + t_b / s_b)
+    sample = ('user side: all %d pairs of the first %d example users in %.1fs; business side: all '
+              '%d pairs of %d seeded-random candidate businesses in %.1fs; combined as '
+              '1/(t_u/S_u+t_b/S_b); %d processes; graph load untimed' %
+              (s_u, n_user_groups, t_u, s_b, n_biz_groups, t_b, procs))
+    _G = None
+    _EX = None
+    return rate, sample, {'user_pairs_per_s': s_u / t_u, 'business_pairs_per_s': s_b / t_b}
+
+
+def _cpu_worker_packed(args):
+    side, ex = args
+    from oracle import similarity_oracle as oa
+    t = time.perf_counter()
+    oa.business(ex, _G, METHODS, [None] * 3, write=False)
+    return time.perf_counter() - t
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            f = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+# ------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--config', default='C2')
+    ap.add_argument('--pairs', type=int, default=None, help='pairs per GPU (default: config)')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-user-groups', type=int, default=None)
+    ap.add_argument('--cpu-biz-groups', type=int, default=None)
+    a = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world == 1 and a.gpus > 1 and 'RANK' not in os.environ:
+        # convenience: re-launch ourselves under torchrun
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+               '--nproc-per-node', str(a.gpus), '--master-addr', '127.0.0.1', '--master-port',
+               os.environ.get('MASTER_PORT', '29511')] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    if a.warmup < 3 and a.impl == 'b200':
+        a.warmup = 3
+
+    synth = pkg('synth')
+    cfg = dict(synth.CONFIGS[a.config])
+    per_gpu = a.pairs or cfg['n_pairs']
+    workload = ('%s: %d users x %d businesses, %d review lines, %d candidate pairs per GPU '
+                '(K=%d per example user), seeded synthetic Yelp-shaped' %
+                (a.config, cfg['n_users'], cfg['n_biz'], cfg['n_reviews'], per_gpu, cfg['k']))
+    config = {'workload': workload, 'name': a.config, 'pairs_per_gpu': per_gpu,
+              'outputs_per_pair': 9, 'l2': 'L2 flushed (256 MiB write) before every timed step',
+              'sharding': 'adjacency replicated, contiguous user-aligned pair shards'}
+    cores = len(os.sched_getaffinity(0))
+
+    # every rank generates the same graph; its own pair shard
+    eu, eb = synth.make_graph(seed=0, **cfg)
+    deg = synth.degrees(cfg['n_users'], cfg['n_biz'], eu, eb)
+    pcfg = dict(cfg)
+    pcfg['n_pairs'] = per_gpu * world
+    pu, pv = synth.make_pairs(edge_u=eu, edge_b=eb, seed=1, rank=rank, world=world, deg=deg,
+                              **pcfg)
+
+    ug = a.cpu_user_groups or 600 * cores
+    bg = a.cpu_biz_groups or 1000 * cores
+
+    if a.impl == 'reference':
+        if rank != 0:
+            return
+        t0 = time.perf_counter()
+        vals = []
+        for _ in range(max(1, min(a.steps, 2))):
+            rate, sample, sides = cpu_reference(cfg, eu, eb, pu, pv, ug, bg, cores)
+            vals.append(rate)
+        rate = statistics.median(vals)
+        line = {'metric': METRIC, 'value': rate, 'unit': UNIT, 'impl': 'reference',
+                'n_gpus': a.gpus, 'steps': len(vals), 'warmup': 0,
+                'ms_per_step': (time.perf_counter() - t0) * 1e3 / len(vals),
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64',
+                'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                 'sample': sample, 'note': NOTE, 'sides': sides},
+                'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        # before CUDA is initialised in this process (the baseline forks workers)
+        rate, sample, sides = cpu_reference(cfg, eu, eb, pu, pv, ug, bg, cores)
+        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                        'sample': sample, 'note': NOTE, 'sides': sides}
+
+    import torch
+    import torch.distributed as dist
+    graph, roofline, _lib = pkg('graph'), pkg('roofline'), pkg('_lib')
+    _lib.load()   # fails loudly when the CUDA extension is missing
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, device=local_rank)
+    n = int(pu.size)
+    d_u = torch.from_numpy(pu).to(dev)
+    d_b = torch.from_numpy(pv).to(dev)
+    out_u = out_b = None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        nonlocal out_u, out_b
+        out_u = G.score_side(_lib.SIDE_USER, d_u, d_b, want_pa=True, out=out_u)
+        out_b = G.score_side(_lib.SIDE_BUSINESS, d_u, d_b, out=out_b)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        flush.zero_()
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3 if sampler else 0.0)
+    total_ms, score_ms_u, score_ms_b, group_ms = 0.0, [], [], []
+    launches = 0
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        su, sb = G.score_stats(_lib.SIDE_USER), G.score_stats(_lib.SIDE_BUSINESS)
+        score_ms_u.append(su['score_ms'])
+        score_ms_b.append(sb['score_ms'])
+        group_ms.append(su['group_ms'] + sb['group_ms'])
+        launches += su['kernel_launches'] + sb['kernel_launches']
+    barrier()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.window(t_wall0, t_wall1) if sampler else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / a.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    # ---- final gather of the result records over NCCL (north_star), timed on its own
+    gather = None
+    if world > 1:
+        keys_u = ['cn', 'union', 'jaccard', 'adamic', 'pa']
+        keys_b = ['cn', 'union', 'jaccard', 'adamic']
+        srcs = [out_u[k] for k in keys_u] + [out_b[k] for k in keys_b]
+        dsts = [[torch.empty_like(s) for _ in range(world)] if rank == 0 else None for s in srcs]
+        for _ in range(2):
+            for s, d in zip(srcs, dsts):
+                dist.gather(s, d, dst=0)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for s, d in zip(srcs, dsts):
+            dist.gather(s, d, dst=0)
+        g1.record()
+        torch.cuda.synchronize()
+        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        gms = float(gt.item())
+        gather = {'ms': gms, 'bytes_into_rank0': 56 * n * (world - 1),
+                  'value_with_gather': n * world / ((ms_per_step + gms) * 1e-3), 'unit': UNIT,
+                  'backend': 'nccl gather, not overlapped'}
+        del dsts
+
+    # ---- end to end through the host-buffer API
+    sess = G.host_session(n)
+    hu, hb = sess.pinned_inputs(n)
+    hu[:] = pu
+    hb[:] = pv
+    e2e_steps = max(3, min(a.steps, 10))
+    for _ in range(2):
+        sess.score_pinned(n)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host = sess.score_pinned(n)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_s = float(dt.item()) / e2e_steps
+    e2e = {'value': n * world / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
+           'h2d_bytes_per_step': sess.h2d_bytes_per_pair * n,
+           'd2h_bytes_per_step': sess.d2h_bytes_per_pair * n, 'steps': e2e_steps,
+           'api': 'BipartiteGraph.host_session().score_pinned -> blp_score_pairs (both sides)'}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        ab = roofline.algorithmic_bytes(cfg['n_users'], cfg['n_biz'], eu, eb, pu, pv,
+                                        host['u_cn'], host['b_cn'])
+        ku_ms = statistics.mean(score_ms_u)
+        kb_ms = statistics.mean(score_ms_b)
+        bytes_u = ab['user'] + ab['pa']
+        ach = bytes_u / (ku_ms * 1e-3) / 1e9
+        roof = {'bound': 'hbm', 'kernel': 'k_score_side<user side> (two-hop expansion + '
+                'intersection + epilogue, PA folded in)',
+                'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks
+                else 'fallback 6650 GB/s (of fallback)',
+                'traffic': None, 'algorithmic_bytes_per_launch': bytes_u,
+                'kernel_ms': ku_ms,
+                'business_kernel': {'kernel_ms': kb_ms, 'algorithmic_bytes_per_launch':
+                                    ab['business'],
+                                    'achieved': ab['business'] / (kb_ms * 1e-3) / 1e9},
+                'grouping_ms_per_step': statistics.mean(group_ms),
+                'whole_step': {'algorithmic_bytes': ab['total'],
+                               'achieved': ab['total'] / (ms_per_step * 1e-3) / 1e9},
+                'bytes_breakdown': {k: ab[k] for k in ('expansion_user', 'stream_user',
+                                                       'expansion_business', 'stream_business',
+                                                       'pa', 'invalid')}}
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps,
+                'warmup': a.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic',
+                'config': config, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
+                'roofline': roof, 'cpu_baseline': cpu_baseline, 'gather': gather,
+                'graph': G.info()}
+        print(json.dumps(line), flush=True)
+    if sampler:
+        sampler.stop()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

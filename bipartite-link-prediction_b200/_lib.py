@@ -40,7 +40,8 @@ class ScoreStats(ctypes.Structure):
     _fields_ = [('n_pairs', ctypes.c_int64), ('n_groups', ctypes.c_int64),
                 ('kernel_launches', ctypes.c_int32), ('ctas', ctypes.c_int32),
                 ('threads_per_cta', ctypes.c_int32), ('smem_bytes', ctypes.c_int32),
-                ('range_passes', ctypes.c_int32)]
+                ('range_passes', ctypes.c_int32), ('group_ms', ctypes.c_float),
+                ('score_ms', ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

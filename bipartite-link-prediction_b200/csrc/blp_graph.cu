@@ -205,6 +205,11 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
             g->sm_count = prop.multiProcessorCount;
             g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
         }
+        for (int sd = 0; sd < 2 && rc == BLP_OK; ++sd)
+            for (int k = 0; k < 3 && rc == BLP_OK; ++k) {
+                e = cudaEventCreate(&g->ev[sd][k]);
+                if (e != cudaSuccess) rc = blp::cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
+            }
         if (rc == BLP_OK) rc = blp::upload(&g->u_off, u_off, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->b_off, b_off, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->u_adj, u_adj, &g->device_bytes);
@@ -239,6 +244,9 @@ extern "C" int blp_graph_destroy(blp_graph* g) {
     cudaFree(g->b_deg);
     cudaFree(g->u_w);
     cudaFree(g->b_w);
+    for (int sd = 0; sd < 2; ++sd)
+        for (int k = 0; k < 3; ++k)
+            if (g->ev[sd][k]) cudaEventDestroy(g->ev[sd][k]);
     (void)cudaGetLastError();
     delete g;
     return BLP_OK;
@@ -281,5 +289,11 @@ extern "C" int blp_score_stats(const blp_graph* g, int side, blp_score_stats_t* 
         return BLP_ERR_INVALID;
     }
     *stats = g->stats[side];
+    if (g->ev_recorded[side]) {
+        BLP_CUDA_TRY(cudaSetDevice(g->device));
+        BLP_CUDA_TRY(cudaEventSynchronize(g->ev[side][2]));
+        BLP_CUDA_TRY(cudaEventElapsedTime(&stats->group_ms, g->ev[side][0], g->ev[side][1]));
+        BLP_CUDA_TRY(cudaEventElapsedTime(&stats->score_ms, g->ev[side][1], g->ev[side][2]));
+    }
     return BLP_OK;
 }

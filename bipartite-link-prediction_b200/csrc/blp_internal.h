@@ -31,6 +31,8 @@ struct blp_graph {
     long long* u_w = nullptr;    // Q24.40 1/ln(deg), 0 where deg <= 1
     long long* b_w = nullptr;
     blp_score_stats_t stats[2] = {};
+    cudaEvent_t ev[2][3] = {};   // per side: start, after grouping, after scoring
+    bool ev_recorded[2] = {false, false};
 };
 
 namespace blp {

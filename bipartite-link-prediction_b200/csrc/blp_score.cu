@@ -428,6 +428,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     blp_score_stats_t& stats = g->stats[side];
     stats = blp_score_stats_t{};
     stats.n_pairs = n;
+    g->ev_recorded[side] = false;
     if (n == 0) return BLP_OK;
 
     const bool us = side == BLP_SIDE_USER;
@@ -478,6 +479,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     BLP_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
     BLP_CUDA_TRY(cudaMemsetAsync(scalars, 0, sizeof(int) * 2, st));
 
+    BLP_CUDA_TRY(cudaEventRecord(g->ev[side][0], st));
     const int gblocks = (int)std::min<long long>((n + 255) / 256, (long long)g->sm_count * 16);
     k_group_count<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, a.g_deg, a.m_deg, cnt);
     BLP_CUDA_TRY(cudaGetLastError());
@@ -486,6 +488,8 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     k_group_scatter<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, a.g_deg, a.m_deg, grp_off,
                                              cursor, perm);
     BLP_CUDA_TRY(cudaGetLastError());
+
+    BLP_CUDA_TRY(cudaEventRecord(g->ev[side][1], st));
 
     a.grp_off = grp_off;
     a.item_key = item_key;
@@ -515,6 +519,8 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         if (nt == 256) rc = launch_side<256>(a, grid, smem, st);
         else if (nt == 512) rc = launch_side<512>(a, grid, smem, st);
         else rc = launch_side<1024>(a, grid, smem, st);
+        if (rc == BLP_OK && cudaEventRecord(g->ev[side][2], st) == cudaSuccess)
+            g->ev_recorded[side] = true;
         stats.ctas = grid;
         stats.threads_per_cta = nt;
         stats.smem_bytes = (int)smem;

@@ -257,7 +257,87 @@ class BipartiteGraph(object):
             host = {k: v.cpu().numpy() for k, v in res.items()}
         return host
 
+    def host_session(self, max_pairs):
+        """Reusable pinned/device buffers for repeated host-to-host scoring of <= max_pairs."""
+        return HostSession(self, max_pairs)
+
     def score_id_pairs(self, ids_u, ids_b, want_hop2=False):
         """Same, for ids of the reference's shared id space (unknown ids score 0)."""
         return self.score_pairs_host(self.local_users(ids_u), self.local_businesses(ids_b),
                                      want_hop2=want_hop2)
+
+
+class HostSession(object):
+    """End-to-end scoring with HOST buffers: pinned staging, H2D of the pair ids, both sides on
+    the device, D2H of all outputs (56 B per pair), overlapped on two streams.
+
+    The business side runs first; the user side (the long one) then overlaps with the D2H of the
+    business-side results, and only the user-side copy-back is exposed at the end.
+    """
+
+    KEYS = ('u_cn', 'u_union', 'u_jaccard', 'u_adamic', 'b_cn', 'b_union', 'b_jaccard',
+            'b_adamic', 'pa')
+    DTYPES = {'cn': torch.int32, 'union': torch.int32, 'jaccard': torch.float64,
+              'adamic': torch.float64, 'pa': torch.int64}
+
+    def __init__(self, graph, max_pairs):
+        self.g, self.n_max = graph, int(max_pairs)
+        dev = graph.device
+        n = self.n_max
+        self.h_u = torch.empty(n, dtype=torch.int32).pin_memory()
+        self.h_b = torch.empty(n, dtype=torch.int32).pin_memory()
+        self.d_u = torch.empty(n, dtype=torch.int32, device=dev)
+        self.d_b = torch.empty(n, dtype=torch.int32, device=dev)
+        self.d_out, self.h_out = {}, {}
+        for k in self.KEYS:
+            dt = self.DTYPES[k.split('_')[-1]]
+            self.d_out[k] = torch.empty(n, dtype=dt, device=dev)
+            self.h_out[k] = torch.empty(n, dtype=dt).pin_memory()
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.h2d_bytes_per_pair = 8
+        self.d2h_bytes_per_pair = sum(self.d_out[k].element_size() for k in self.KEYS)
+
+    def pinned_inputs(self, n):
+        """Numpy views of the pinned pair buffers, for callers that fill them in place."""
+        return self.h_u[:n].numpy(), self.h_b[:n].numpy()
+
+    def score(self, pair_u, pair_b):
+        """pair_u / pair_b: host int32 numpy arrays (local indices).  Returns {key: numpy view
+        of the pinned result buffer} -- valid until the next call."""
+        n = int(pair_u.size)
+        if n > self.n_max or pair_b.size != n:
+            raise ValueError('pair count %d exceeds the session capacity %d' % (n, self.n_max))
+        hu, hb = self.pinned_inputs(n)
+        hu[:] = pair_u
+        hb[:] = pair_b
+        return self.score_pinned(n)
+
+    def score_pinned(self, n):
+        """Score the first n pairs already sitting in the pinned input buffers."""
+        n = int(n)
+        if n > self.n_max:
+            raise ValueError('pair count %d exceeds the session capacity %d' % (n, self.n_max))
+        g, dev = self.g, self.g.device
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            du, db = self.d_u[:n], self.d_b[:n]
+            du.copy_(self.h_u[:n], non_blocking=True)
+            db.copy_(self.h_b[:n], non_blocking=True)
+            ob = {k[2:]: self.d_out[k][:n] for k in self.KEYS if k.startswith('b_')}
+            ou = {k[2:]: self.d_out[k][:n] for k in self.KEYS if k.startswith('u_')}
+            ou['pa'] = self.d_out['pa'][:n]
+            g.score_side(_lib.SIDE_BUSINESS, du, db, out=ob)
+            ev_b = torch.cuda.Event()
+            ev_b.record(main)
+            g.score_side(_lib.SIDE_USER, du, db, want_pa=True, out=ou)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(ev_b)
+                for k in self.KEYS:
+                    if k.startswith('b_'):
+                        self.h_out[k][:n].copy_(self.d_out[k][:n], non_blocking=True)
+            for k in self.KEYS:
+                if not k.startswith('b_'):
+                    self.h_out[k][:n].copy_(self.d_out[k][:n], non_blocking=True)
+            main.wait_stream(self.copy_stream)
+            main.synchronize()
+        return {k: self.h_out[k][:n].numpy() for k in self.KEYS}

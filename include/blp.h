@@ -70,6 +70,8 @@ typedef struct blp_score_stats_t {
     int32_t threads_per_cta;
     int32_t smem_bytes;       /* dynamic shared memory per CTA */
     int32_t range_passes;     /* id-range passes over the hop-2 bitmap (1 = fits shared memory) */
+    float group_ms;           /* CUDA-event time of the grouping kernels (count, scan, scatter) */
+    float score_ms;           /* CUDA-event time of the scoring kernel alone, on its own stream */
 } blp_score_stats_t;
 
 int blp_version(void);
@@ -119,7 +121,8 @@ int blp_score_pairs(blp_graph* g, int side,
                     int32_t* cn, int32_t* uni, double* jaccard, double* adamic,
                     int64_t* pa, int32_t* hop2_size, void* stream);
 
-/* Accounting of the most recent blp_score_pairs on this handle (per side). */
+/* Accounting of the most recent blp_score_pairs on this handle (per side).  The two event times
+ * are valid once that call's work has completed (the function waits for its end event). */
 int blp_score_stats(const blp_graph* g, int side, blp_score_stats_t* stats);
 
 #ifdef __cplusplus
