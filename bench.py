@@ -228,7 +228,7 @@ def main():
                               **pcfg)
 
     ug = a.cpu_user_groups or 600 * cores
-    bg = a.cpu_biz_groups or 1000 * cores
+    bg = a.cpu_biz_groups or 250 * cores
 
     if a.impl == 'reference':
         if rank != 0:

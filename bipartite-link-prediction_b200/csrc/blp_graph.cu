@@ -193,6 +193,18 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
             g->n_biz_in += d > 0;
             g->max_bdeg = std::max(g->max_bdeg, d);
         }
+        // packed row descriptors
+        if (u_off[n_users] / 4 >= (1LL << 40) || b_off[n_biz] / 4 >= (1LL << 40) ||
+            g->max_udeg >= (1 << 24) || g->max_bdeg >= (1 << 24)) {
+            delete g;
+            blp::set_error("blp_graph_create: graph too large for the packed row descriptors");
+            return BLP_ERR_UNSUPPORTED;
+        }
+        std::vector<unsigned long long> u_row((size_t)n_users), b_row((size_t)n_biz);
+        for (int32_t u = 0; u < n_users; ++u)
+            u_row[u] = ((unsigned long long)(u_off[u] >> 2) << 24) | (unsigned)u_deg[u];
+        for (int32_t b = 0; b < n_biz; ++b)
+            b_row[b] = ((unsigned long long)(b_off[b] >> 2) << 24) | (unsigned)b_deg[b];
         std::vector<long long> u_w, b_w;
         blp::weights_from_degrees(u_deg, g->max_udeg, u_w);
         blp::weights_from_degrees(b_deg, g->max_bdeg, b_w);
@@ -210,8 +222,8 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
                 e = cudaEventCreate(&g->ev[sd][k]);
                 if (e != cudaSuccess) rc = blp::cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
             }
-        if (rc == BLP_OK) rc = blp::upload(&g->u_off, u_off, &g->device_bytes);
-        if (rc == BLP_OK) rc = blp::upload(&g->b_off, b_off, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->u_row, u_row, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->b_row, b_row, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->u_adj, u_adj, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->b_adj, b_adj, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->u_deg, u_deg, &g->device_bytes);
@@ -236,8 +248,8 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
 extern "C" int blp_graph_destroy(blp_graph* g) {
     if (!g) return BLP_OK;
     cudaSetDevice(g->device);
-    cudaFree(g->u_off);
-    cudaFree(g->b_off);
+    cudaFree(g->u_row);
+    cudaFree(g->b_row);
     cudaFree(g->u_adj);
     cudaFree(g->b_adj);
     cudaFree(g->u_deg);

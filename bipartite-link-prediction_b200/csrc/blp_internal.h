@@ -19,11 +19,12 @@ struct blp_graph {
     int64_t n_edges_in = 0, n_edges = 0;
     int32_t n_users_in = 0, n_biz_in = 0, max_udeg = 0, max_bdeg = 0;
     int64_t device_bytes = 0;
-    // Both CSR directions.  Row offsets count PADDED entries: every row is padded to a multiple of
+    // Both CSR directions.  Every row is padded to a multiple of
     // four ids with the sentinel n_biz (user rows) / n_users (business rows), so every row starts
     // 16-byte aligned and is read with 128-bit loads without a tail.
-    long long* u_off = nullptr;  // [n_users+1]
-    long long* b_off = nullptr;  // [n_biz+1]
+    // Row descriptors: (first padded entry / 4) << 24 | true degree -- one 8-byte load per list.
+    unsigned long long* u_row = nullptr;  // [n_users]
+    unsigned long long* b_row = nullptr;  // [n_biz]
     int* u_adj = nullptr;        // user -> businesses, ascending
     int* b_adj = nullptr;        // business -> users, ascending
     int* u_deg = nullptr;        // true (unpadded, de-duplicated) degrees

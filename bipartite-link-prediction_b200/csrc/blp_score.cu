@@ -27,13 +27,12 @@ constexpr int kChunkV4 = 128;     // int4 loads per chunk (4 per lane): 512 ids
 constexpr unsigned kFull = 0xffffffffu;
 
 struct SideArgs {
-    // grouping side x: rows x -> middle nodes m;   middle side: rows m -> nodes of x's side
-    const long long* __restrict__ g_off;
+    // grouping side x: rows x -> middle nodes m;   middle side: rows m -> nodes of x's side.
+    // A row descriptor packs (first entry / 4) << 24 | degree: one 8-byte load locates a list.
+    const unsigned long long* __restrict__ g_row;
     const int* __restrict__ g_adj;
-    const long long* __restrict__ m_off;
+    const unsigned long long* __restrict__ m_row;
     const int* __restrict__ m_adj;
-    const int* __restrict__ g_deg;
-    const int* __restrict__ m_deg;
     const long long* __restrict__ g_w;   // Q24.40 weights of x-side nodes
     int n_side;                           // number of x-side nodes == sentinel id of m rows
     int bm_words;                         // bitmap words (covers bit n_side as well)
@@ -41,8 +40,8 @@ struct SideArgs {
     const long long* __restrict__ grp_off;  // [n_side + 2]; key n_side = "not in graph"
     const int* __restrict__ item_key;       // non-empty group keys
     const int* __restrict__ n_items;
-    const int* __restrict__ perm;           // pair indices ordered by group
-    const int* __restrict__ partner;        // y of every pair, caller order
+    const int* __restrict__ perm;           // caller-order pair index, grouped order
+    const int* __restrict__ gpartner;       // partner y of every pair, grouped order
     int* work_counter;
     // outputs, caller order (any may be null)
     int* cn;
@@ -60,6 +59,9 @@ __device__ __forceinline__ int4 ldg_stream(const int4* p) {
                  : "l"(p));
     return r;
 }
+
+__device__ __forceinline__ int row_deg(unsigned long long row) { return (int)(row & 0xffffffull); }
+__device__ __forceinline__ long long row_first4(unsigned long long row) { return (long long)(row >> 24); }
 
 // ---------------------------------------------------------------------------------------------
 // Grouping: counting sort of pair indices by the node whose hop-2 set they need.
@@ -148,30 +150,33 @@ __global__ void k_group_scatter(const int* __restrict__ gx, const int* __restric
                                 long long n, int n_side, int n_mid,
                                 const int* __restrict__ g_deg, const int* __restrict__ m_deg,
                                 const long long* __restrict__ grp_off,
-                                unsigned* __restrict__ cursor, int* __restrict__ perm) {
+                                unsigned* __restrict__ cursor, int* __restrict__ perm,
+                                int* __restrict__ gpartner) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        int key = group_key(gx[i], gy[i], n_side, n_mid, g_deg, m_deg);
-        unsigned pos = atomicAdd(&cursor[key], 1u);
-        perm[grp_off[key] + pos] = (int)i;
+        int y = gy[i];
+        int key = group_key(gx[i], y, n_side, n_mid, g_deg, m_deg);
+        long long pos = grp_off[key] + atomicAdd(&cursor[key], 1u);
+        perm[pos] = (int)i;
+        gpartner[pos] = y;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // The scoring kernel.
 // ---------------------------------------------------------------------------------------------
+constexpr int kShortV4 = 4;   // lists of <= 16 ids take the sub-warp path (4 lanes per list)
+
 struct TileSmem {
-    long long start[kTile];            // first padded entry of the list
+    unsigned long long row[kTile];     // packed row descriptor of every list of the tile
     unsigned long long aa[kTile];      // Q24.40 Adamic-Adar accumulators
-    int n4[kTile];                     // list length in int4 units
-    int scan[kTile + 8];               // exclusive prefix of chunk counts, [kTile] = total
+    int scan[kTile + 8];               // exclusive prefix of long-list chunk counts, [kTile] = total
     int cn[kTile];
     int idx[kTile];                    // caller-order pair index
-    int pdeg[kTile];                   // true degree of the partner
     int wsum[32];
     int red[32];
-    int item;
+    int item_next;
     int hop2;
 };
 
@@ -206,11 +211,119 @@ __device__ __forceinline__ int find_list(const TileSmem& ts, int c, int lane) {
     return kb * 8 + __popc(__ballot_sync(kFull, v2 <= c)) - 1;
 }
 
-__device__ __forceinline__ void set_bit(unsigned* bm, int id) {
-    unsigned bit = 1u << (id & 31);
-    unsigned* w = bm + (id >> 5);
-    // bits are only ever set during expansion, so a stale read can only cause a redundant atomic
-    if (!(*(volatile unsigned*)w & bit)) atomicOr(w, bit);
+// The three things done to a streamed id.
+//   OP_SET  plain read-modify-write of the bitmap word.  Concurrent writers of one word can lose
+//           each other's bits (shared-memory atomics cost ~2 cycles per lane and dominated the
+//           first version of this kernel), so a barrier and an OP_FIX sweep follow.
+//   OP_FIX  re-walks the same ids and repairs any lost bit with an atomic (rare).
+//   OP_TEST membership test of the intersection phase.
+enum { OP_SET = 0, OP_FIX = 1, OP_TEST = 2 };
+
+template <int OP>
+__device__ __forceinline__ void touch(unsigned* bm, int id, const long long* __restrict__ w_tab,
+                                      int& cnt, unsigned long long& acc) {
+    const unsigned bit = 1u << (id & 31);
+    volatile unsigned* w = bm + (id >> 5);
+    if (OP == OP_SET) {
+        unsigned old = *w;
+        if (!(old & bit)) *w = old | bit;
+    } else if (OP == OP_FIX) {
+        if (!(*w & bit)) atomicOr(const_cast<unsigned*>(w), bit);
+    } else {
+        if (*w & bit) {
+            ++cnt;
+            acc += (unsigned long long)__ldg(w_tab + id);
+        }
+    }
+}
+
+template <int OP>
+__device__ __forceinline__ void touch4(unsigned* bm, int4 v, const long long* __restrict__ w_tab,
+                                       int& cnt, unsigned long long& acc) {
+    touch<OP>(bm, v.x, w_tab, cnt, acc);
+    touch<OP>(bm, v.y, w_tab, cnt, acc);
+    touch<OP>(bm, v.z, w_tab, cnt, acc);
+    touch<OP>(bm, v.w, w_tab, cnt, acc);
+}
+
+// Walks the `count` adjacency lists described by ts.row[] (ts.scan[] already holds the chunk
+// prefix of the long ones).  Short lists: 4 lanes per list, 8 lists per warp pass.  Long lists:
+// 512-id chunks dealt round-robin to warps, so a hub list is spread over the whole CTA.
+template <int NT, int OP>
+__device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, TileSmem& ts,
+                                           int count, int lane, int warp) {
+    constexpr int NW = NT / 32;
+    const int4* adj4 = reinterpret_cast<const int4*>(a.m_adj);
+    const int4 sent4 = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
+    // ---- short lists
+    {
+        const int sub = lane & 3, slot = lane >> 2;
+        for (int base = warp * 8; base < count; base += NW * 8) {
+            const int j = base + slot;
+            const unsigned long long row = j < count ? ts.row[j] : 0ull;
+            const int n4 = (row_deg(row) + 3) >> 2;
+            const bool is_short = n4 > 0 && n4 <= kShortV4;
+            const bool mine = is_short && sub < n4;
+            if (!__any_sync(kFull, mine)) continue;
+            int cnt = 0;
+            unsigned long long acc = 0ull;
+            if (mine) {
+                int4 v = ldg_stream(adj4 + row_first4(row) + sub);
+                touch4<OP>(bm, v, a.g_w, cnt, acc);
+            }
+            if (OP == OP_TEST) {
+                cnt += __shfl_xor_sync(kFull, cnt, 1);
+                cnt += __shfl_xor_sync(kFull, cnt, 2);
+                if (__any_sync(kFull, cnt > 0)) {
+                    acc += __shfl_xor_sync(kFull, acc, 1);
+                    acc += __shfl_xor_sync(kFull, acc, 2);
+                }
+                if (is_short && sub == 0) {
+                    ts.cn[j] = cnt;
+                    ts.aa[j] = acc;
+                }
+            }
+        }
+    }
+    // ---- long lists
+    const int total = ts.scan[kTile];
+    for (int c = warp; c < total; c += NW) {
+        const int j = find_list(ts, c, lane);
+        const unsigned long long row = ts.row[j];
+        const int off4 = (c - ts.scan[j]) * kChunkV4;
+        const int n = min(kChunkV4, ((row_deg(row) + 3) >> 2) - off4);
+        const int4* p = adj4 + row_first4(row) + off4;
+        int4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int i = lane + 32 * k;
+            v[k] = i < n ? ldg_stream(p + i) : sent4;
+        }
+        int cnt = 0;
+        unsigned long long acc = 0ull;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (32 * k < n) {
+                if (OP == OP_TEST || lane + 32 * k < n) touch4<OP>(bm, v[k], a.g_w, cnt, acc);
+            }
+        }
+        if (OP == OP_TEST) {
+            if (__any_sync(kFull, cnt > 0)) {
+                cnt = __reduce_add_sync(kFull, cnt);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
+                if (lane == 0) {
+                    atomicAdd(&ts.cn[j], cnt);
+                    atomicAdd(&ts.aa[j], acc);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int long_chunks(unsigned long long row) {
+    const int n4 = (row_deg(row) + 3) >> 2;
+    return n4 > kShortV4 ? (n4 + kChunkV4 - 1) / kChunkV4 : 0;
 }
 
 template <int NT>
@@ -221,14 +334,16 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
     const int n_items = *a.n_items;
-    const int4 sent4 = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
 
+    if (tid == 0) ts.item_next = atomicAdd(a.work_counter, 1);
     for (;;) {
-        __syncthreads();   // previous item fully retired (ts.item, bitmap, tile arrays)
-        if (tid == 0) ts.item = atomicAdd(a.work_counter, 1);
+        __syncthreads();   // previous item fully retired; ts.item_next published
+        const int item = ts.item_next;
         __syncthreads();
-        const int item = ts.item;
         if (item >= n_items) break;
+        // claim the next item now; its latency hides behind this group's work
+        int claimed = 0;
+        if (tid == 0) claimed = atomicAdd(a.work_counter, 1);
         const int x = a.item_key[item];
         const long long p0 = a.grp_off[x], p1 = a.grp_off[x + 1];
 
@@ -243,6 +358,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
                 if (a.pa) a.pa[idx] = 0;
                 if (a.hop2) a.hop2[idx] = 0;
             }
+            if (tid == 0) ts.item_next = claimed;
             continue;
         }
 
@@ -252,45 +368,24 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
             const int n4 = a.bm_words >> 2;   // bm_words is a multiple of 4
             for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
         }
-        const int xdeg = a.g_deg[x];
-        const long long xrow = a.g_off[x];
+        const unsigned long long xrow = a.g_row[x];
+        const int xdeg = row_deg(xrow);
+        const int* xadj = a.g_adj + row_first4(xrow) * 4;
         __syncthreads();
 
         // ---- phase 1: two-hop expansion, hop2(x) |= N(m) for every m in N(x)
         for (int tb = 0; tb < xdeg; tb += kTile) {
+            const int count = min(kTile, xdeg - tb);
             int nch = 0;
-            if (tid < kTile) {
-                int li = tb + tid;
-                if (li < xdeg) {
-                    int m = a.g_adj[xrow + li];
-                    long long s = a.m_off[m], e = a.m_off[m + 1];
-                    int n4 = (int)((e - s) >> 2);
-                    ts.start[tid] = s;
-                    ts.n4[tid] = n4;
-                    nch = (n4 + kChunkV4 - 1) / kChunkV4;
-                }
+            if (tid < count) {
+                unsigned long long row = a.m_row[xadj[tb + tid]];
+                ts.row[tid] = row;
+                nch = long_chunks(row);
             }
             tile_scan<NT>(ts, nch, tid);
-            const int total = ts.scan[kTile];
-            for (int c = warp; c < total; c += NW) {
-                int j = find_list(ts, c, lane);
-                int off4 = (c - ts.scan[j]) * kChunkV4;
-                int n = min(kChunkV4, ts.n4[j] - off4);
-                const int4* p = reinterpret_cast<const int4*>(a.m_adj + ts.start[j]) + off4;
-                int4 v[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int i = lane + 32 * k;
-                    v[k] = i < n ? ldg_stream(p + i) : sent4;
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    set_bit(bm, v[k].x);
-                    set_bit(bm, v[k].y);
-                    set_bit(bm, v[k].z);
-                    set_bit(bm, v[k].w);
-                }
-            }
+            sweep_tile<NT, OP_SET>(a, bm, ts, count, lane, warp);
+            __syncthreads();
+            sweep_tile<NT, OP_FIX>(a, bm, ts, count, lane, warp);
             __syncthreads();
         }
 
@@ -318,66 +413,24 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
 
         // ---- phase 3: every pair (x, y) of the group: stream N(y), test, count, weigh
         for (long long tb = p0; tb < p1; tb += kTile) {
+            const int count = (int)min((long long)kTile, p1 - tb);
             int nch = 0;
-            if (tid < kTile) {
-                long long k = tb + tid;
-                if (k < p1) {
-                    int idx = a.perm[k];
-                    int y = a.partner[idx];
-                    long long s = a.m_off[y], e = a.m_off[y + 1];
-                    int n4 = (int)((e - s) >> 2);
-                    ts.start[tid] = s;
-                    ts.n4[tid] = n4;
-                    ts.idx[tid] = idx;
-                    ts.pdeg[tid] = a.m_deg[y];
-                    ts.cn[tid] = 0;
-                    ts.aa[tid] = 0ull;
-                    nch = (n4 + kChunkV4 - 1) / kChunkV4;
-                }
+            if (tid < count) {
+                unsigned long long row = a.m_row[a.gpartner[tb + tid]];
+                ts.row[tid] = row;
+                ts.idx[tid] = a.perm[tb + tid];
+                ts.cn[tid] = 0;
+                ts.aa[tid] = 0ull;
+                nch = long_chunks(row);
             }
             tile_scan<NT>(ts, nch, tid);
-            const int total = ts.scan[kTile];
-            for (int c = warp; c < total; c += NW) {
-                int j = find_list(ts, c, lane);
-                int off4 = (c - ts.scan[j]) * kChunkV4;
-                int n = min(kChunkV4, ts.n4[j] - off4);
-                const int4* p = reinterpret_cast<const int4*>(a.m_adj + ts.start[j]) + off4;
-                int4 v[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int i = lane + 32 * k;
-                    v[k] = i < n ? ldg_stream(p + i) : sent4;
-                }
-                int cnt = 0;
-                unsigned long long acc = 0ull;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int ids[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        int id = ids[q];
-                        if ((bm[id >> 5] >> (id & 31)) & 1u) {
-                            ++cnt;
-                            acc += (unsigned long long)__ldg(a.g_w + id);
-                        }
-                    }
-                }
-                if (__any_sync(kFull, cnt > 0)) {
-                    cnt = __reduce_add_sync(kFull, cnt);
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
-                    if (lane == 0) {
-                        atomicAdd(&ts.cn[j], cnt);
-                        atomicAdd(&ts.aa[j], acc);
-                    }
-                }
-            }
+            sweep_tile<NT, OP_TEST>(a, bm, ts, count, lane, warp);
             __syncthreads();
             // epilogue: one thread per pair of the tile
-            if (tid < kTile && tb + tid < p1) {
+            if (tid < count) {
                 int idx = ts.idx[tid];
                 int c = ts.cn[tid];
-                int pdeg = ts.pdeg[tid];
+                int pdeg = row_deg(ts.row[tid]);
                 int u = hop2 + pdeg - c;   // |a| + |b| - |a & b|  (similarity.py:110)
                 if (a.cn) a.cn[idx] = c;
                 if (a.uni) a.uni[idx] = u;
@@ -388,6 +441,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
             }
             __syncthreads();
         }
+        if (tid == 0) ts.item_next = claimed;
     }
 }
 
@@ -433,18 +487,17 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
 
     const bool us = side == BLP_SIDE_USER;
     SideArgs a{};
-    a.g_off = us ? g->u_off : g->b_off;
+    a.g_row = (const unsigned long long*)(us ? g->u_row : g->b_row);
     a.g_adj = us ? g->u_adj : g->b_adj;
-    a.m_off = us ? g->b_off : g->u_off;
+    a.m_row = (const unsigned long long*)(us ? g->b_row : g->u_row);
     a.m_adj = us ? g->b_adj : g->u_adj;
-    a.g_deg = us ? g->u_deg : g->b_deg;
-    a.m_deg = us ? g->b_deg : g->u_deg;
+    const int* g_deg = us ? g->u_deg : g->b_deg;
+    const int* m_deg = us ? g->b_deg : g->u_deg;
     a.g_w = us ? g->u_w : g->b_w;
     a.n_side = us ? g->n_users : g->n_biz;
     const int n_mid = us ? g->n_biz : g->n_users;
     const int* gx = us ? pair_u : pair_b;
     const int* gy = us ? pair_b : pair_u;
-    a.partner = gy;
     a.cn = cn;
     a.uni = uni;
     a.jac = jaccard;
@@ -469,24 +522,25 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     const int n_keys = a.n_side + 1;
     unsigned *cnt = nullptr, *cursor = nullptr;
     long long* grp_off = nullptr;
-    int *item_key = nullptr, *perm = nullptr, *scalars = nullptr;
+    int *item_key = nullptr, *perm = nullptr, *gpartner = nullptr, *scalars = nullptr;
     BLP_CUDA_TRY(cudaMallocAsync((void**)&cnt, sizeof(unsigned) * (size_t)n_keys, st));
     BLP_CUDA_TRY(cudaMallocAsync((void**)&cursor, sizeof(unsigned) * (size_t)n_keys, st));
     BLP_CUDA_TRY(cudaMallocAsync((void**)&grp_off, sizeof(long long) * ((size_t)n_keys + 1), st));
     BLP_CUDA_TRY(cudaMallocAsync((void**)&item_key, sizeof(int) * (size_t)n_keys, st));
     BLP_CUDA_TRY(cudaMallocAsync((void**)&perm, sizeof(int) * (size_t)n, st));
+    BLP_CUDA_TRY(cudaMallocAsync((void**)&gpartner, sizeof(int) * (size_t)n, st));
     BLP_CUDA_TRY(cudaMallocAsync((void**)&scalars, sizeof(int) * 2, st));
     BLP_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
     BLP_CUDA_TRY(cudaMemsetAsync(scalars, 0, sizeof(int) * 2, st));
 
     BLP_CUDA_TRY(cudaEventRecord(g->ev[side][0], st));
     const int gblocks = (int)std::min<long long>((n + 255) / 256, (long long)g->sm_count * 16);
-    k_group_count<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, a.g_deg, a.m_deg, cnt);
+    k_group_count<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, g_deg, m_deg, cnt);
     BLP_CUDA_TRY(cudaGetLastError());
     k_group_scan<<<1, 1024, 0, st>>>(cnt, n_keys, grp_off, cursor, item_key, scalars);
     BLP_CUDA_TRY(cudaGetLastError());
-    k_group_scatter<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, a.g_deg, a.m_deg, grp_off,
-                                             cursor, perm);
+    k_group_scatter<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, g_deg, m_deg, grp_off,
+                                             cursor, perm, gpartner);
     BLP_CUDA_TRY(cudaGetLastError());
 
     BLP_CUDA_TRY(cudaEventRecord(g->ev[side][1], st));
@@ -496,6 +550,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     a.n_items = scalars;
     a.work_counter = scalars + 1;
     a.perm = perm;
+    a.gpartner = gpartner;
 
     // ---- persistent scoring grid: as many CTAs per SM as the bitmap allows
     int per_sm = 0, nt = 0, rc = BLP_OK;
@@ -532,6 +587,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     cudaFreeAsync(grp_off, st);
     cudaFreeAsync(item_key, st);
     cudaFreeAsync(perm, st);
+    cudaFreeAsync(gpartner, st);
     cudaFreeAsync(scalars, st);
     return rc;
 }
