@@ -74,15 +74,18 @@ static void padded_offsets(int32_t n_rows, const std::vector<int32_t>& deg,
     for (int32_t r = 0; r < n_rows; ++r) off[r + 1] = off[r] + (((long long)deg[r] + 3) & ~3LL);
 }
 
-static void weights_from_degrees(const std::vector<int32_t>& deg, int32_t max_deg,
-                                 std::vector<long long>& w) {
-    // 1/ln(deg) once per distinct degree with the host libm (the kernels do no transcendental
-    // math), rounded to Q24.40.  deg <= 1 contributes 0 (similarity.py:122-125).
-    std::vector<long long> lut((size_t)max_deg + 1, 0);
+// Per-entry weights: adjw[k] = Q1.31(1 / ln(deg(adj[k]))), with the degree taken on the side the
+// entry names.  1/ln(deg) is evaluated once per distinct degree with the host libm (the kernels
+// do no transcendental math); deg <= 1 contributes 0 (similarity.py:122-125), padding too.
+static void entry_weights(const std::vector<int32_t>& adj, int32_t sentinel,
+                          const std::vector<int32_t>& deg_of_entry_side, int32_t max_deg,
+                          std::vector<unsigned>& adjw) {
+    std::vector<unsigned> lut((size_t)max_deg + 1, 0u);
     for (int32_t d = 2; d <= max_deg; ++d)
-        lut[d] = llrint(ldexp(1.0 / log((double)d), BLP_AA_FRAC_BITS));
-    w.resize(deg.size());
-    for (size_t i = 0; i < deg.size(); ++i) w[i] = lut[deg[i]];
+        lut[d] = (unsigned)llrint(ldexp(1.0 / log((double)d), BLP_AA_FRAC_BITS));
+    adjw.resize(adj.size());
+    for (size_t k = 0; k < adj.size(); ++k)
+        adjw[k] = adj[k] == sentinel ? 0u : lut[deg_of_entry_side[adj[k]]];
 }
 }  // namespace blp
 
@@ -205,9 +208,9 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
             u_row[u] = ((unsigned long long)(u_off[u] >> 2) << 24) | (unsigned)u_deg[u];
         for (int32_t b = 0; b < n_biz; ++b)
             b_row[b] = ((unsigned long long)(b_off[b] >> 2) << 24) | (unsigned)b_deg[b];
-        std::vector<long long> u_w, b_w;
-        blp::weights_from_degrees(u_deg, g->max_udeg, u_w);
-        blp::weights_from_degrees(b_deg, g->max_bdeg, b_w);
+        std::vector<unsigned> u_adjw, b_adjw;
+        blp::entry_weights(u_adj, n_biz, b_deg, g->max_bdeg, u_adjw);   // user rows name businesses
+        blp::entry_weights(b_adj, n_users, u_deg, g->max_udeg, b_adjw); // business rows name users
 
         cudaDeviceProp prop;
         rc = BLP_OK;
@@ -216,6 +219,16 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
         if (rc == BLP_OK) {
             g->sm_count = prop.multiProcessorCount;
             g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+        }
+        if (rc == BLP_OK) {
+            // keep stream-ordered scratch cached in the pool instead of returning it to the
+            // driver at every synchronisation (the default release threshold is 0)
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            (void)cudaGetLastError();
         }
         for (int sd = 0; sd < 2 && rc == BLP_OK; ++sd)
             for (int k = 0; k < 3 && rc == BLP_OK; ++k) {
@@ -228,8 +241,8 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
         if (rc == BLP_OK) rc = blp::upload(&g->b_adj, b_adj, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->u_deg, u_deg, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->b_deg, b_deg, &g->device_bytes);
-        if (rc == BLP_OK) rc = blp::upload(&g->u_w, u_w, &g->device_bytes);
-        if (rc == BLP_OK) rc = blp::upload(&g->b_w, b_w, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->u_adjw, u_adjw, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::upload(&g->b_adjw, b_adjw, &g->device_bytes);
         if (rc != BLP_OK) {
             std::string keep = blp_last_error();
             blp_graph_destroy(g);
@@ -254,8 +267,8 @@ extern "C" int blp_graph_destroy(blp_graph* g) {
     cudaFree(g->b_adj);
     cudaFree(g->u_deg);
     cudaFree(g->b_deg);
-    cudaFree(g->u_w);
-    cudaFree(g->b_w);
+    cudaFree(g->u_adjw);
+    cudaFree(g->b_adjw);
     for (int sd = 0; sd < 2; ++sd)
         for (int k = 0; k < 3; ++k)
             if (g->ev[sd][k]) cudaEventDestroy(g->ev[sd][k]);

@@ -8,8 +8,9 @@
 
 #include "blp.h"
 
-// Q24.40 fixed point for the Adamic-Adar weights: integer sums are order independent.
-#define BLP_AA_FRAC_BITS 40
+// Fixed point for the Adamic-Adar weights: integer sums are order independent.  A weight is at
+// most 1/ln 2 = 1.4427 < 2, so Q1.31 fits 32 bits; sums are kept in 64 bits.
+#define BLP_AA_FRAC_BITS 31
 
 struct blp_graph {
     int device = 0;
@@ -29,8 +30,10 @@ struct blp_graph {
     int* b_adj = nullptr;        // business -> users, ascending
     int* u_deg = nullptr;        // true (unpadded, de-duplicated) degrees
     int* b_deg = nullptr;
-    long long* u_w = nullptr;    // Q24.40 1/ln(deg), 0 where deg <= 1
-    long long* b_w = nullptr;
+    // Adamic-Adar weight 1/ln(deg(id)) (0 where deg <= 1 and in padding) of every adjacency
+    // entry, Q1.31, parallel to u_adj / b_adj: the weight streams in beside the id it belongs to.
+    unsigned* u_adjw = nullptr;
+    unsigned* b_adjw = nullptr;
     blp_score_stats_t stats[2] = {};
     cudaEvent_t ev[2][3] = {};   // per side: start, after grouping, after scoring
     bool ev_recorded[2] = {false, false};

@@ -33,7 +33,7 @@ struct SideArgs {
     const int* __restrict__ g_adj;
     const unsigned long long* __restrict__ m_row;
     const int* __restrict__ m_adj;
-    const long long* __restrict__ g_w;   // Q24.40 weights of x-side nodes
+    const unsigned* __restrict__ m_adjw;  // Q1.31 Adamic-Adar weight of every m_adj entry
     int n_side;                           // number of x-side nodes == sentinel id of m rows
     int bm_words;                         // bitmap words (covers bit n_side as well)
     // grouping
@@ -219,31 +219,41 @@ __device__ __forceinline__ int find_list(const TileSmem& ts, int c, int lane) {
 //   OP_TEST membership test of the intersection phase.
 enum { OP_SET = 0, OP_FIX = 1, OP_TEST = 2 };
 
+__device__ __forceinline__ uint4 ldg_stream_u(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
 template <int OP>
-__device__ __forceinline__ void touch(unsigned* bm, int id, const long long* __restrict__ w_tab,
-                                      int& cnt, unsigned long long& acc) {
-    const unsigned bit = 1u << (id & 31);
+__device__ __forceinline__ void touch(unsigned* bm, int id, unsigned wt, unsigned& cnt,
+                                      unsigned long long& acc) {
     volatile unsigned* w = bm + (id >> 5);
     if (OP == OP_SET) {
+        const unsigned bit = 1u << (id & 31);
         unsigned old = *w;
         if (!(old & bit)) *w = old | bit;
     } else if (OP == OP_FIX) {
+        const unsigned bit = 1u << (id & 31);
         if (!(*w & bit)) atomicOr(const_cast<unsigned*>(w), bit);
     } else {
-        if (*w & bit) {
-            ++cnt;
-            acc += (unsigned long long)__ldg(w_tab + id);
-        }
+        // branch-free: the weight rides in the stream next to the id, so a hit costs one
+        // integer multiply-add (IMAD.WIDE) instead of a divergent 8-byte gather
+        const unsigned hit = (*w >> (id & 31)) & 1u;
+        cnt += hit;
+        acc += (unsigned long long)hit * (unsigned long long)wt;
     }
 }
 
 template <int OP>
-__device__ __forceinline__ void touch4(unsigned* bm, int4 v, const long long* __restrict__ w_tab,
-                                       int& cnt, unsigned long long& acc) {
-    touch<OP>(bm, v.x, w_tab, cnt, acc);
-    touch<OP>(bm, v.y, w_tab, cnt, acc);
-    touch<OP>(bm, v.z, w_tab, cnt, acc);
-    touch<OP>(bm, v.w, w_tab, cnt, acc);
+__device__ __forceinline__ void touch4(unsigned* bm, int4 v, uint4 wt, unsigned& cnt,
+                                       unsigned long long& acc) {
+    touch<OP>(bm, v.x, wt.x, cnt, acc);
+    touch<OP>(bm, v.y, wt.y, cnt, acc);
+    touch<OP>(bm, v.z, wt.z, cnt, acc);
+    touch<OP>(bm, v.w, wt.w, cnt, acc);
 }
 
 // Walks the `count` adjacency lists described by ts.row[] (ts.scan[] already holds the chunk
@@ -254,7 +264,9 @@ __device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, Tile
                                            int count, int lane, int warp) {
     constexpr int NW = NT / 32;
     const int4* adj4 = reinterpret_cast<const int4*>(a.m_adj);
+    const uint4* adjw4 = reinterpret_cast<const uint4*>(a.m_adjw);
     const int4 sent4 = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     // ---- short lists
     {
         const int sub = lane & 3, slot = lane >> 2;
@@ -265,11 +277,13 @@ __device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, Tile
             const bool is_short = n4 > 0 && n4 <= kShortV4;
             const bool mine = is_short && sub < n4;
             if (!__any_sync(kFull, mine)) continue;
-            int cnt = 0;
+            unsigned cnt = 0;
             unsigned long long acc = 0ull;
             if (mine) {
-                int4 v = ldg_stream(adj4 + row_first4(row) + sub);
-                touch4<OP>(bm, v, a.g_w, cnt, acc);
+                const long long at = row_first4(row) + sub;
+                int4 v = ldg_stream(adj4 + at);
+                uint4 wt = OP == OP_TEST ? ldg_stream_u(adjw4 + at) : zero4;
+                touch4<OP>(bm, v, wt, cnt, acc);
             }
             if (OP == OP_TEST) {
                 cnt += __shfl_xor_sync(kFull, cnt, 1);
@@ -279,7 +293,7 @@ __device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, Tile
                     acc += __shfl_xor_sync(kFull, acc, 2);
                 }
                 if (is_short && sub == 0) {
-                    ts.cn[j] = cnt;
+                    ts.cn[j] = (int)cnt;
                     ts.aa[j] = acc;
                 }
             }
@@ -292,19 +306,21 @@ __device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, Tile
         const unsigned long long row = ts.row[j];
         const int off4 = (c - ts.scan[j]) * kChunkV4;
         const int n = min(kChunkV4, ((row_deg(row) + 3) >> 2) - off4);
-        const int4* p = adj4 + row_first4(row) + off4;
+        const long long at = row_first4(row) + off4;
         int4 v[4];
+        uint4 wt[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             int i = lane + 32 * k;
-            v[k] = i < n ? ldg_stream(p + i) : sent4;
+            v[k] = i < n ? ldg_stream(adj4 + at + i) : sent4;
+            wt[k] = (OP == OP_TEST && i < n) ? ldg_stream_u(adjw4 + at + i) : zero4;
         }
-        int cnt = 0;
+        unsigned cnt = 0;
         unsigned long long acc = 0ull;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (32 * k < n) {
-                if (OP == OP_TEST || lane + 32 * k < n) touch4<OP>(bm, v[k], a.g_w, cnt, acc);
+                if (OP == OP_TEST || lane + 32 * k < n) touch4<OP>(bm, v[k], wt[k], cnt, acc);
             }
         }
         if (OP == OP_TEST) {
@@ -313,7 +329,7 @@ __device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, Tile
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
                 if (lane == 0) {
-                    atomicAdd(&ts.cn[j], cnt);
+                    atomicAdd(&ts.cn[j], (int)cnt);
                     atomicAdd(&ts.aa[j], acc);
                 }
             }
@@ -392,7 +408,15 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
         // ---- phase 2: |hop2(x)| = popcount minus x itself and the padding sentinel
         {
             int c = 0;
-            for (int i = tid; i < a.bm_words; i += NT) c += __popc(bm[i]);
+            {
+                const uint4* b4 = reinterpret_cast<const uint4*>(bm);
+                const int n4 = a.bm_words >> 2;
+#pragma unroll 4
+                for (int i = tid; i < n4; i += NT) {
+                    uint4 q = b4[i];
+                    c += __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
+                }
+            }
             c = __reduce_add_sync(kFull, c);
             int adj = 0;
             if (tid == 0) {
@@ -493,7 +517,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     a.m_adj = us ? g->b_adj : g->u_adj;
     const int* g_deg = us ? g->u_deg : g->b_deg;
     const int* m_deg = us ? g->b_deg : g->u_deg;
-    a.g_w = us ? g->u_w : g->b_w;
+    a.m_adjw = us ? g->b_adjw : g->u_adjw;
     a.n_side = us ? g->n_users : g->n_biz;
     const int n_mid = us ? g->n_biz : g->n_users;
     const int* gx = us ? pair_u : pair_b;

@@ -108,8 +108,8 @@ int blp_graph_degrees(const blp_graph* g, int side, int32_t* host_out);
  *   uni       int32   |hop2(x) | N(y)|                      (similarity.py:110), bit-exact
  *   jaccard   double  (double)cn / (double)uni, div.rn       (similarity.py:108-111), bit-exact
  *   adamic    double  sum over matched i with deg(i)>1 of 1/ln(deg(i)) (similarity.py:116-126);
- *                     accumulated in 2^-40 fixed point so the result does not depend on
- *                     summation order, bucket or rank count (|err| <= cn*2^-41, rel <= 1e-11)
+ *                     accumulated in 2^-31 fixed point so the result does not depend on
+ *                     summation order, bucket or rank count (|err| <= cn*2^-32, rel <= 4e-9)
  *   pa        int64   deg(u)*deg(v)  ("Link prediction.R":400-415); may be NULL
  *   hop2_size int32   |hop2(x)| of the pair's grouping node; may be NULL (debug / tests)
  * with x = user, y = business for side USER and x = business, y = user for side BUSINESS.
