@@ -17,12 +17,16 @@
 // warp pass each (degree-bucketed scheduling without separate launches).
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 
 #include "blp_internal.h"
 
 namespace blp {
 
-constexpr int kTile = 256;        // adjacency lists per scheduling tile
+#ifndef BLP_TILE
+#define BLP_TILE 256
+#endif
+constexpr int kTile = BLP_TILE;   // adjacency lists per scheduling tile (<= threads per CTA)
 constexpr int kChunkV4 = 128;     // int4 loads per chunk (4 per lane): 512 ids
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -172,6 +176,8 @@ struct TileSmem {
     unsigned long long row[kTile];     // packed row descriptor of every list of the tile
     unsigned long long aa[kTile];      // Q24.40 Adamic-Adar accumulators
     int scan[kTile + 8];               // exclusive prefix of long-list chunk counts, [kTile] = total
+    int coarse[32];                    // scan[8*i], contiguous: conflict-free first probe
+    int next_chunk[4];                 // dynamic chunk dispensers, one per sweep kind (OP_*)
     int cn[kTile];
     int idx[kTile];                    // caller-order pair index
     int wsum[32];
@@ -195,17 +201,27 @@ __device__ __forceinline__ void tile_scan(TileSmem& ts, int v, int tid) {
     }
     __syncthreads();
     if (tid < kTile) {
-        int base = 0;
-        for (int w = 0; w < warp; ++w) base += ts.wsum[w];
-        ts.scan[tid] = base + inc - v;
+        // prefix over the kTile/32 warp totals, computed redundantly by every warp
+        int wv = lane < kTile / 32 ? ts.wsum[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < kTile / 32; d <<= 1) {
+            int t = __shfl_up_sync(kFull, wv, d);
+            if (lane >= d) wv += t;
+        }
+        int base = __shfl_sync(kFull, wv, max(warp, 1) - 1);
+        if (warp == 0) base = 0;
+        const int ex = base + inc - v;
+        ts.scan[tid] = ex;
+        if ((tid & 7) == 0) ts.coarse[tid >> 3] = ex;
         if (tid == kTile - 1) ts.scan[kTile] = base + inc;
+        if (tid < 4) ts.next_chunk[tid] = 0;
     }
     __syncthreads();
 }
 
 // Which list owns chunk c?  Two 32-wide probes of the 257-entry prefix array (warp-uniform c).
 __device__ __forceinline__ int find_list(const TileSmem& ts, int c, int lane) {
-    int v = ts.scan[lane * 8];
+    int v = lane < kTile / 8 ? ts.coarse[lane] : INT_MAX;
     int kb = __popc(__ballot_sync(kFull, v <= c)) - 1;
     int v2 = lane < 8 ? ts.scan[kb * 8 + lane] : INT_MAX;
     return kb * 8 + __popc(__ballot_sync(kFull, v2 <= c)) - 1;
@@ -301,7 +317,11 @@ __device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, Tile
     }
     // ---- long lists
     const int total = ts.scan[kTile];
-    for (int c = warp; c < total; c += NW) {
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&ts.next_chunk[OP], 1);
+        c = __shfl_sync(kFull, c, 0);
+        if (c >= total) break;
         const int j = find_list(ts, c, lane);
         const unsigned long long row = ts.row[j];
         const int off4 = (c - ts.scan[j]) * kChunkV4;
@@ -324,13 +344,19 @@ __device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, Tile
             }
         }
         if (OP == OP_TEST) {
-            if (__any_sync(kFull, cnt > 0)) {
+            const bool single = ((row_deg(row) + 3) >> 2) <= kChunkV4;   // whole list in this chunk
+            if (single || __any_sync(kFull, cnt > 0)) {
                 cnt = __reduce_add_sync(kFull, cnt);
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
                 if (lane == 0) {
-                    atomicAdd(&ts.cn[j], (int)cnt);
-                    atomicAdd(&ts.aa[j], acc);
+                    if (single) {
+                        ts.cn[j] = (int)cnt;
+                        ts.aa[j] = acc;
+                    } else {
+                        atomicAdd(&ts.cn[j], (int)cnt);
+                        atomicAdd(&ts.aa[j], acc);
+                    }
                 }
             }
         }
@@ -342,8 +368,27 @@ __device__ __forceinline__ int long_chunks(unsigned long long row) {
     return n4 > kShortV4 ? (n4 + kChunkV4 - 1) / kChunkV4 : 0;
 }
 
+#ifdef BLP_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define BLP_TICK(slot)                                                        \
+    do {                                                                      \
+        if (tid == 0) {                                                       \
+            long long now__ = clock64();                                      \
+            atomicAdd(&g_phase_cycles[slot], (unsigned long long)(now__ - t_last)); \
+            t_last = now__;                                                   \
+        }                                                                     \
+    } while (0)
+#else
+#define BLP_TICK(slot) do {} while (0)
+#endif
+
+#ifndef BLP_THREADS_PER_SM
+#define BLP_THREADS_PER_SM 1024
+#endif
+
 template <int NT>
-__global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
+__global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREADS_PER_SM / NT) : 1)
+    k_score_side(SideArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned* bm = reinterpret_cast<unsigned*>(smem_raw);
     TileSmem& ts = *reinterpret_cast<TileSmem*>(smem_raw + (size_t)a.bm_words * 4);
@@ -351,9 +396,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
     constexpr int NW = NT / 32;
     const int n_items = *a.n_items;
 
+#ifdef BLP_PHASE_TIMING
+    long long t_last = clock64();
+#endif
     if (tid == 0) ts.item_next = atomicAdd(a.work_counter, 1);
     for (;;) {
         __syncthreads();   // previous item fully retired; ts.item_next published
+        BLP_TICK(0);
         const int item = ts.item_next;
         __syncthreads();
         if (item >= n_items) break;
@@ -388,6 +437,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
         const int xdeg = row_deg(xrow);
         const int* xadj = a.g_adj + row_first4(xrow) * 4;
         __syncthreads();
+        BLP_TICK(1);
 
         // ---- phase 1: two-hop expansion, hop2(x) |= N(m) for every m in N(x)
         for (int tb = 0; tb < xdeg; tb += kTile) {
@@ -399,10 +449,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
                 nch = long_chunks(row);
             }
             tile_scan<NT>(ts, nch, tid);
+            BLP_TICK(2);
             sweep_tile<NT, OP_SET>(a, bm, ts, count, lane, warp);
             __syncthreads();
+            BLP_TICK(3);
             sweep_tile<NT, OP_FIX>(a, bm, ts, count, lane, warp);
             __syncthreads();
+            BLP_TICK(4);
         }
 
         // ---- phase 2: |hop2(x)| = popcount minus x itself and the padding sentinel
@@ -434,6 +487,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
             __syncthreads();
         }
         const int hop2 = ts.hop2;
+        BLP_TICK(5);
 
         // ---- phase 3: every pair (x, y) of the group: stream N(y), test, count, weigh
         for (long long tb = p0; tb < p1; tb += kTile) {
@@ -448,8 +502,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
                 nch = long_chunks(row);
             }
             tile_scan<NT>(ts, nch, tid);
+            BLP_TICK(6);
             sweep_tile<NT, OP_TEST>(a, bm, ts, count, lane, warp);
             __syncthreads();
+            BLP_TICK(7);
             // epilogue: one thread per pair of the tile
             if (tid < count) {
                 int idx = ts.idx[tid];
@@ -464,6 +520,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_score_side(SideArgs a) {
                 if (a.hop2) a.hop2[idx] = hop2;
             }
             __syncthreads();
+            BLP_TICK(8);
         }
         if (tid == 0) ts.item_next = claimed;
     }
@@ -579,7 +636,21 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     // ---- persistent scoring grid: as many CTAs per SM as the bitmap allows
     int per_sm = 0, nt = 0, rc = BLP_OK;
     const size_t budget = (size_t)g->max_smem_optin;
-    if (smem * 4 + 4096 <= budget) {
+    const char* nt_env = getenv("BLP_NT");   // tuning override
+    const int nt_force = nt_env ? atoi(nt_env) : 0;
+    if (nt_force == 128 && kTile <= 128) {
+        nt = 128;
+        rc = occupancy<128>(smem, &per_sm);
+    } else if (nt_force == 384) {
+        nt = 384;
+        rc = occupancy<384>(smem, &per_sm);
+    } else if (nt_force == 512) {
+        nt = 512;
+        rc = occupancy<512>(smem, &per_sm);
+    } else if (nt_force == 1024) {
+        nt = 1024;
+        rc = occupancy<1024>(smem, &per_sm);
+    } else if (smem * 4 + 4096 <= budget) {
         nt = 256;
         rc = occupancy<256>(smem, &per_sm);
     } else if (smem * 2 + 2048 <= budget) {
@@ -595,7 +666,9 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     }
     if (rc == BLP_OK) {
         const int grid = per_sm * g->sm_count;
-        if (nt == 256) rc = launch_side<256>(a, grid, smem, st);
+        if (nt == 128) rc = launch_side<128>(a, grid, smem, st);
+        else if (nt == 256) rc = launch_side<256>(a, grid, smem, st);
+        else if (nt == 384) rc = launch_side<384>(a, grid, smem, st);
         else if (nt == 512) rc = launch_side<512>(a, grid, smem, st);
         else rc = launch_side<1024>(a, grid, smem, st);
         if (rc == BLP_OK && cudaEventRecord(g->ev[side][2], st) == cudaSuccess)
@@ -615,3 +688,15 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     cudaFreeAsync(scalars, st);
     return rc;
 }
+
+#ifdef BLP_PHASE_TIMING
+extern "C" int blp_debug_phase_cycles(unsigned long long* host_out16, int reset) {
+    BLP_CUDA_TRY(cudaDeviceSynchronize());
+    BLP_CUDA_TRY(cudaMemcpyFromSymbol(host_out16, blp::g_phase_cycles, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {};
+        BLP_CUDA_TRY(cudaMemcpyToSymbol(blp::g_phase_cycles, z, sizeof(z)));
+    }
+    return BLP_OK;
+}
+#endif
