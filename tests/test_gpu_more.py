@@ -1,0 +1,141 @@
+"""More GPU parity: golden fixtures, file-level drop-in, C2-sized sample, sharding, stress shapes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, pkg
+from test_gpu_parity import AA_KEYS, INT_KEYS, JAC_KEYS, check_against, mods  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_cases(mods):
+    graph, synth = mods
+    cases = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'cases.json')))['cases']
+    for c in cases:
+        G = graph.BipartiteGraph(c['n_users'], c['n_biz'], c['edge_u'], c['edge_b'])
+        got = G.score_pairs_host(np.array(c['pair_u'], np.int32), np.array(c['pair_b'], np.int32))
+        check_against(got, c['expect'], len(c['pair_u']))
+
+
+def test_file_level_drop_in_matches_oracle_files(mods, tmp_path):
+    """similarity.main(...) writes the same six JSON files the reference's main would."""
+    from oracle import similarity_oracle as oa
+    graph, synth = mods
+    sim, util = pkg('similarity'), pkg('util')
+    eu, eb = synth.make_graph(300, 60, 1200, seed=21, shift_u=1.0, shift_b=2.0)
+    pu, pv = synth.make_pairs(300, 60, eu, eb, 900, k=6, seed=22, invalid_frac=0.03)
+    ids_eu, ids_eb = synth.shared_ids(300, eu, eb)
+    ids_pu, ids_pv = synth.shared_ids(300, pu, pv)
+    util.write_edge_list(str(tmp_path / 'graph.txt'), ids_eu, ids_eb)
+    util.write_json(synth.examples_dict(ids_pu, ids_pv), str(tmp_path / 'examples.json'))
+    M = ['common_neighbors', 'jaccard', 'adamic_adar']
+    names = ('cn', 'jaccard', 'adamic')
+    for bug in (False, True):
+        mine = [[str(tmp_path / ('%s_%s_mine%d.json' % (s, n, bug))) for n in names] for s in 'ub']
+        ref = [[str(tmp_path / ('%s_%s_ref%d.json' % (s, n, bug))) for n in names] for s in 'ub']
+        sim.main(str(tmp_path / 'examples.json'), str(tmp_path / 'graph.txt'), M, mine[0], M,
+                 mine[1], reproduce_reference_bug=bug)
+        oa.main(str(tmp_path / 'examples.json'), str(tmp_path / 'graph.txt'), M, ref[0], M, ref[1],
+                reproduce_reference_bug=bug)
+        for fm, fr in zip(mine[0] + mine[1], ref[0] + ref[1]):
+            a, b = util.load_json(fm), util.load_json(fr)
+            assert a.keys() == b.keys(), fm
+            for u in a:
+                assert a[u].keys() == b[u].keys(), (fm, u)
+                for v in a[u]:
+                    x, y = a[u][v], b[u][v]
+                    assert type(x) is type(y), (fm, u, v, x, y)     # int 0 vs float, as the reference
+                    if 'adamic' in fm:
+                        assert x == pytest.approx(y, rel=1e-6), (fm, u, v)
+                    else:
+                        assert x == y, (fm, u, v)
+
+
+def test_c2_sample_vs_c_oracle(mods):
+    """BASELINE.json configs[1] graph (366k x 61k, 1.5M reviews), 300k-pair sample, C oracle."""
+    from oracle import c_oracle
+    graph, synth = mods
+    cfg, eu, eb, pu, pv = synth.make_config('C2', n_pairs=300_000)
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    got = G.score_pairs_host(pu, pv)
+    want = c_oracle.score_pair_arrays(cfg['n_users'], cfg['n_biz'], eu, eb, pu, pv)
+    check_against(got, want, pu.size)
+
+
+def test_shards_equal_whole(mods):
+    """Emulated ranks on one GPU: scoring user-aligned slices == scoring the whole list."""
+    graph, synth = mods
+    d = pkg('dist')
+    cfg, eu, eb, pu, pv = synth.make_config('C1', n_pairs=40_000)
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    whole = G.score_pairs_host(pu, pv)
+    du, db = synth.degrees(cfg['n_users'], cfg['n_biz'], eu, eb)
+    for world in (2, 8):
+        b = d.shard_bounds(pu, world, d.pair_costs(pu, pv, du, db))
+        parts = [G.score_pairs_host(pu[b[r]:b[r + 1]], pv[b[r]:b[r + 1]]) for r in range(world)]
+        for k in whole:
+            assert np.array_equal(np.concatenate([p[k] for p in parts]), whole[k]), (world, k)
+
+
+def test_hub_rows_and_big_groups(mods):
+    """Lists longer than one 512-id chunk, a user with more than 256 businesses (several
+    expansion tiles) and a business with more than 256 candidate pairs (several pair tiles)."""
+    from oracle import c_oracle
+    graph, synth = mods
+    rng = np.random.default_rng(9)
+    n_users, n_biz = 6000, 700
+    eu = [rng.integers(0, n_users, 9000)]
+    eb = [rng.integers(0, n_biz, 9000)]
+    eu.append(np.arange(0, 3000))                    # business 0: hub with 3000 users (6 chunks)
+    eb.append(np.zeros(3000, np.int64))
+    eu.append(np.full(600, 7))                       # user 7: 600 businesses (3 expansion tiles)
+    eb.append(np.arange(0, 600))
+    eu, eb = np.concatenate(eu), np.concatenate(eb)
+    pu = np.concatenate([rng.integers(0, n_users, 4000), np.full(700, 7), rng.integers(0, n_users, 900)])
+    pv = np.concatenate([rng.integers(0, n_biz, 4000), np.arange(700), np.zeros(900, np.int64)])
+    G = graph.BipartiteGraph(n_users, n_biz, eu, eb)
+    got = G.score_pairs_host(pu, pv)
+    want = c_oracle.score_pair_arrays(n_users, n_biz, eu, eb, pu, pv)
+    check_against(got, want, pu.size)
+
+
+@pytest.mark.timeout(600)
+def test_full_c2_properties(mods):
+    """Full BASELINE.json configs[1] size (10M pairs): size-independent properties."""
+    import torch
+    graph, synth = mods
+    lib = pkg('_lib')
+    cfg, eu, eb, pu, pv = synth.make_config('C2')
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    du, dv = torch.from_numpy(pu).cuda(), torch.from_numpy(pv).cuda()
+    r = G.score_pairs(du, dv, want_hop2=True)
+    deg_u = torch.from_numpy(G.degrees(lib.SIDE_USER)).cuda().long()
+    deg_b = torch.from_numpy(G.degrees(lib.SIDE_BUSINESS)).cuda().long()
+    ok = (du >= 0) & (dv >= 0)
+    ok &= (deg_u[du.clamp(min=0).long()] > 0) & (deg_b[dv.clamp(min=0).long()] > 0)
+    u, v = du[ok].long(), dv[ok].long()
+    # union = |hop2| + deg(partner) - cn, both sides; pa = deg(u)*deg(v)
+    assert torch.equal(r['u_union'][ok].long(), r['u_hop2'][ok].long() + deg_b[v] - r['u_cn'][ok].long())
+    assert torch.equal(r['b_union'][ok].long(), r['b_hop2'][ok].long() + deg_u[u] - r['b_cn'][ok].long())
+    assert torch.equal(r['pa'][ok], deg_u[u] * deg_b[v])
+    # jaccard == cn/union bit-exactly in fp64
+    assert torch.equal(r['u_jaccard'][ok], r['u_cn'][ok].double() / r['u_union'][ok].double())
+    assert torch.equal(r['b_jaccard'][ok], r['b_cn'][ok].double() / r['b_union'][ok].double())
+    # bounds: 0 <= cn <= min(|hop2|, deg(partner)); aa <= cn/ln 2; aa == 0 needs cn weights 0
+    assert bool((r['u_cn'][ok].long() <= torch.minimum(r['u_hop2'][ok].long(), deg_b[v])).all())
+    assert bool((r['b_cn'][ok].long() <= torch.minimum(r['b_hop2'][ok].long(), deg_u[u])).all())
+    assert bool((r['u_adamic'] <= r['u_cn'].double() / np.log(2.0) + 1e-9).all())
+    # "no length-3 path" is seen from both sides alike when u is not adjacent to v:
+    # u_cn == 0 and b_cn == 0 can differ only for existing edges
+    differ = (r['u_cn'][ok] == 0) != (r['b_cn'][ok] == 0)
+    assert int(differ.sum()) <= int(ok.sum()) // 100
+    # pairs with an id that is not in the graph are all-zero
+    for k, t in r.items():
+        assert not bool(t[~ok].any()), k
+    # same input twice -> bit-identical (no float atomics, order-independent accumulation)
+    r2 = G.score_pairs(du, dv)
+    for k in r2:
+        assert torch.equal(r[k], r2[k]), k
