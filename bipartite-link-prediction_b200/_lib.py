@@ -30,7 +30,9 @@ class GraphInfo(ctypes.Structure):
                 ('n_users_in_graph', ctypes.c_int32), ('n_biz_in_graph', ctypes.c_int32),
                 ('max_user_degree', ctypes.c_int32), ('max_biz_degree', ctypes.c_int32),
                 ('device_bytes', ctypes.c_int64), ('device', ctypes.c_int32),
-                ('sm_count', ctypes.c_int32)]
+                ('sm_count', ctypes.c_int32), ('n_hub_biz', ctypes.c_int32),
+                ('n_hub_users', ctypes.c_int32), ('hub_min_biz_degree', ctypes.c_int32),
+                ('hub_min_user_degree', ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -3,6 +3,7 @@
 // (similarity.py:16, 22, 65, 121).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -72,6 +73,49 @@ static void padded_offsets(int32_t n_rows, const std::vector<int32_t>& deg,
                            std::vector<long long>& off) {
     off.assign((size_t)n_rows + 1, 0);
     for (int32_t r = 0; r < n_rows; ++r) off[r + 1] = off[r] + (((long long)deg[r] + 3) & ~3LL);
+}
+
+// Bank striping.  The kernels probe a shared-memory bitmap with one 32-bit load per id; word
+// id>>5 lives in bank (id>>5)&31, so 32 random ids cost ~3 wavefronts instead of 1.  Nothing in
+// the algorithm needs a row in ascending order, so every row longer than the sub-warp path is
+// permuted once here: the 32 ids that ONE load instruction touches (lane l reads component q of
+// the int4 at index 32*block + l, i.e. slots 128*block + 4*l + q) are drawn from 32 different
+// banks for as long as every bank still has ids left (largest remaining bucket first).
+static void bank_stripe_row(int32_t* row, int len, std::vector<int32_t>& tmp,
+                            std::vector<int32_t> (&bucket)[32]) {
+    for (auto& b : bucket) b.clear();
+    for (int i = 0; i < len; ++i) bucket[(row[i] >> 5) & 31].push_back(row[i]);
+    tmp.assign((size_t)len, 0);
+    const int n4 = (len + 3) >> 2;
+    int order[32];
+    for (int blk = 0; blk * 32 < n4; ++blk) {
+        const int lanes = std::min(32, n4 - blk * 32);
+        for (int q = 0; q < 4; ++q) {
+            // real slots of this wave: lane l is real iff its slot index is < len
+            int cap = 0;
+            for (int l = 0; l < lanes; ++l) cap += (128 * blk + 4 * l + q) < len;
+            if (cap == 0) continue;
+            for (int b = 0; b < 32; ++b) order[b] = b;
+            std::sort(order, order + 32, [&](int a, int b) {
+                return bucket[a].size() > bucket[b].size();
+            });
+            int filled = 0, l = 0;
+            while (filled < cap) {
+                // one id from each of the fullest buckets; wrap around only when fewer than
+                // `cap` buckets are left (then a bank repeats inside the wave)
+                for (int k = 0; k < 32 && filled < cap; ++k) {
+                    std::vector<int32_t>& bk = bucket[order[k]];
+                    if (bk.empty()) continue;
+                    while (l < lanes && (128 * blk + 4 * l + q) >= len) ++l;
+                    tmp[(size_t)(128 * blk + 4 * l + q)] = bk.back();
+                    bk.pop_back();
+                    ++l;
+                    ++filled;
+                }
+            }
+        }
+    }
+    memcpy(row, tmp.data(), sizeof(int32_t) * (size_t)len);
 }
 
 // Per-entry weights: adjw[k] = Q1.31(1 / ln(deg(adj[k]))), with the degree taken on the side the
@@ -181,6 +225,14 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
             }
         }
         std::vector<uint64_t>().swap(keys);
+        if (!getenv("BLP_NO_BANK_STRIPE")) {   // tuning switch
+            std::vector<int32_t> tmp;
+            std::vector<int32_t> bucket[32];
+            for (int32_t u = 0; u < n_users; ++u)
+                if (u_deg[u] > 16) blp::bank_stripe_row(&u_adj[u_off[u]], u_deg[u], tmp, bucket);
+            for (int32_t b = 0; b < n_biz; ++b)
+                if (b_deg[b] > 16) blp::bank_stripe_row(&b_adj[b_off[b]], b_deg[b], tmp, bucket);
+        }
 
         g = new blp_graph();
         g->device = device;
@@ -243,6 +295,7 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
         if (rc == BLP_OK) rc = blp::upload(&g->b_deg, b_deg, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->u_adjw, u_adjw, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->b_adjw, b_adjw, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::build_hub_bitmaps(g, u_deg.data(), b_deg.data());
         if (rc != BLP_OK) {
             std::string keep = blp_last_error();
             blp_graph_destroy(g);
@@ -269,6 +322,10 @@ extern "C" int blp_graph_destroy(blp_graph* g) {
     cudaFree(g->b_deg);
     cudaFree(g->u_adjw);
     cudaFree(g->b_adjw);
+    for (int sd = 0; sd < 2; ++sd) {
+        cudaFree(g->xrow[sd]);
+        cudaFree(g->hub_bm[sd]);
+    }
     for (int sd = 0; sd < 2; ++sd)
         for (int k = 0; k < 3; ++k)
             if (g->ev[sd][k]) cudaEventDestroy(g->ev[sd][k]);
@@ -293,6 +350,10 @@ extern "C" int blp_graph_info(const blp_graph* g, blp_graph_info_t* info) {
     info->device_bytes = g->device_bytes;
     info->device = g->device;
     info->sm_count = g->sm_count;
+    info->n_hub_biz = g->n_hubs[0];
+    info->n_hub_users = g->n_hubs[1];
+    info->hub_min_biz_degree = g->n_hubs[0] ? g->hub_min_deg[0] : 0;
+    info->hub_min_user_degree = g->n_hubs[1] ? g->hub_min_deg[1] : 0;
     return BLP_OK;
 }
 

@@ -34,12 +34,22 @@ struct blp_graph {
     // entry, Q1.31, parallel to u_adj / b_adj: the weight streams in beside the id it belongs to.
     unsigned* u_adjw = nullptr;
     unsigned* b_adjw = nullptr;
+    // Hub bitmaps.  For side s (0 = user side, 1 = business side) the middle nodes of degree >=
+    // hub_min_deg[s] have their whole neighbour list precomputed as a bitmap over the grouping
+    // side, so the two-hop expansion ORs 128-bit words instead of walking the list id by id.
+    unsigned long long* xrow[2] = {nullptr, nullptr};   // expansion-side row descriptors (hubs tagged)
+    unsigned* hub_bm[2] = {nullptr, nullptr};     // [n_hubs][bm_words]
+    int hub_min_deg[2] = {0x7fffffff, 0x7fffffff};
+    int n_hubs[2] = {0, 0};
     blp_score_stats_t stats[2] = {};
     cudaEvent_t ev[2][3] = {};   // per side: start, after grouping, after scoring
     bool ev_recorded[2] = {false, false};
 };
 
 namespace blp {
+// words of the shared-memory bitmap over n_side nodes (+1 sentinel bit), multiple of 4
+inline int bitmap_words(int n_side) { return (int)((((long long)n_side + 1 + 31) / 32 + 3) & ~3LL); }
+int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host);
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 }  // namespace blp

@@ -15,9 +15,11 @@
 // cut into 512-id chunks, the chunk counts are prefix-summed in shared memory and warps take
 // chunks round-robin, so a hub list is spread over the whole CTA while short lists cost one
 // warp pass each (degree-bucketed scheduling without separate launches).
+#include <algorithm>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "blp_internal.h"
 
@@ -40,6 +42,11 @@ struct SideArgs {
     const unsigned* __restrict__ m_adjw;  // Q1.31 Adamic-Adar weight of every m_adj entry
     int n_side;                           // number of x-side nodes == sentinel id of m rows
     int bm_words;                         // bitmap words (covers bit n_side as well)
+    // hub bitmaps: N(m) of every middle node with deg >= hub_min_deg, as bm_words-word bitmaps
+    // m_xrow: row descriptors as seen by the expansion -- equal to m_row except that a hub's
+    // entry is  1<<63 | bitmap slot << 24 | degree  (one gather tells list from bitmap)
+    const unsigned long long* __restrict__ m_xrow;
+    const unsigned* __restrict__ hub_bm;
     // grouping
     const long long* __restrict__ grp_off;  // [n_side + 2]; key n_side = "not in graph"
     const int* __restrict__ item_key;       // non-empty group keys
@@ -180,10 +187,12 @@ struct TileSmem {
     int next_chunk[4];                 // dynamic chunk dispensers, one per sweep kind (OP_*)
     int cn[kTile];
     int idx[kTile];                    // caller-order pair index
+    int hub[kTile];                    // hub-bitmap slots met in the current expansion tile
     int wsum[32];
     int red[32];
     int item_next;
     int hop2;
+    int nhub;
 };
 
 // Exclusive scan of `v` over the first kTile threads into ts.scan[]; ts.scan[kTile] = total.
@@ -399,7 +408,10 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
 #ifdef BLP_PHASE_TIMING
     long long t_last = clock64();
 #endif
-    if (tid == 0) ts.item_next = atomicAdd(a.work_counter, 1);
+    if (tid == 0) {
+        ts.item_next = atomicAdd(a.work_counter, 1);
+        ts.nhub = 0;
+    }
     for (;;) {
         __syncthreads();   // previous item fully retired; ts.item_next published
         BLP_TICK(0);
@@ -427,28 +439,71 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             continue;
         }
 
-        // ---- phase 0: clear the bitmap
-        {
-            uint4* b4 = reinterpret_cast<uint4*>(bm);
-            const int n4 = a.bm_words >> 2;   // bm_words is a multiple of 4
-            for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
         const unsigned long long xrow = a.g_row[x];
         const int xdeg = row_deg(xrow);
         const int* xadj = a.g_adj + row_first4(xrow) * 4;
-        __syncthreads();
-        BLP_TICK(1);
 
-        // ---- phase 1: two-hop expansion, hop2(x) |= N(m) for every m in N(x)
+        // ---- phases 0+1: two-hop expansion, hop2(x) = U N(m) over m in N(x).
+        // Hub lists arrive as precomputed bitmaps and are OR-ed with 128-bit loads by the thread
+        // that owns the word (for the first tile this pass doubles as the clear); every other
+        // list is walked id by id (OP_SET, then OP_FIX after a barrier).
         for (int tb = 0; tb < xdeg; tb += kTile) {
             const int count = min(kTile, xdeg - tb);
             int nch = 0;
             if (tid < count) {
-                unsigned long long row = a.m_row[xadj[tb + tid]];
+                unsigned long long row = a.m_xrow[xadj[tb + tid]];
+                if (row >> 63) {
+                    ts.hub[atomicAdd(&ts.nhub, 1)] = (int)((row >> 24) & 0x7fffffffull);
+                    row = 0ull;                // degree 0: skipped by both list walkers
+                }
                 ts.row[tid] = row;
                 nch = long_chunks(row);
             }
             tile_scan<NT>(ts, nch, tid);
+            BLP_TICK(1);
+            {
+                const int nhub = ts.nhub;
+                uint4* b4 = reinterpret_cast<uint4*>(bm);
+                const uint4* h4 = reinterpret_cast<const uint4*>(a.hub_bm);
+                const int n4 = a.bm_words >> 2;   // bm_words is a multiple of 4
+                if (nhub == 0) {
+                    if (tb == 0)
+                        for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+                    // four independent 128-bit loads in flight per thread and hub
+                    for (int i0 = tid; i0 < n4; i0 += 4 * NT) {
+                        uint4 acc[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = i0 + k * NT;
+                            acc[k] = (tb == 0 || i >= n4) ? make_uint4(0u, 0u, 0u, 0u) : b4[i];
+                        }
+                        for (int h = 0; h < nhub; ++h) {
+                            const uint4* src = h4 + (size_t)ts.hub[h] * n4;
+                            uint4 q[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int i = i0 + k * NT;
+                                q[k] = i < n4 ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                acc[k].x |= q[k].x;
+                                acc[k].y |= q[k].y;
+                                acc[k].z |= q[k].z;
+                                acc[k].w |= q[k].w;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int i = i0 + k * NT;
+                            if (i < n4) b4[i] = acc[k];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) ts.nhub = 0;
             BLP_TICK(2);
             sweep_tile<NT, OP_SET>(a, bm, ts, count, lane, warp);
             __syncthreads();
@@ -543,6 +598,79 @@ static int occupancy(size_t smem, int* ctas_per_sm) {
     return BLP_OK;
 }
 
+// One CTA per hub: write its neighbour list into its (already zeroed) bitmap.
+__global__ void k_build_hub_bitmaps(const int* __restrict__ hub_nodes, int n_hubs,
+                                    const unsigned long long* __restrict__ m_row,
+                                    const int* __restrict__ m_adj, int bm_words,
+                                    unsigned* __restrict__ hub_bm) {
+    for (int h = blockIdx.x; h < n_hubs; h += gridDim.x) {
+        const unsigned long long row = m_row[hub_nodes[h]];
+        const int* adj = m_adj + row_first4(row) * 4;
+        unsigned* bm = hub_bm + (size_t)h * bm_words;
+        for (int i = threadIdx.x; i < row_deg(row); i += blockDim.x) {
+            const int id = adj[i];
+            atomicOr(bm + (id >> 5), 1u << (id & 31));
+        }
+    }
+}
+
+// Picks the hubs of both sides and builds their bitmaps on the device.
+// Cost model (measured on C2, profiles/r01_notes.md): walking a list costs ~0.35 L1 wavefronts per
+// id (two sweeps, bank-conflicted bitmap probes), OR-ing a bitmap costs bm_bytes/128 wavefronts,
+// so a list pays off as a bitmap from deg >= bm_bytes/45 on.
+int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host) {
+    for (int side = 0; side < 2; ++side) {
+        const bool us = side == BLP_SIDE_USER;
+        const int n_side = us ? g->n_users : g->n_biz;     // bitmap universe
+        const int n_mid = us ? g->n_biz : g->n_users;      // hubs are middle nodes
+        const int* mdeg = us ? b_deg_host : u_deg_host;
+        const int words = bitmap_words(n_side);
+        const long long bm_bytes = (long long)words * 4;
+        int min_deg = (int)std::max<long long>(64, bm_bytes / 45);
+        if (const char* e = getenv("BLP_HUB_MIN_DEG")) min_deg = atoi(e);   // tuning override
+        std::vector<int> hubs;
+        if (min_deg > 0)
+            for (int m = 0; m < n_mid; ++m)
+                if (mdeg[m] >= min_deg) hubs.push_back(m);
+        // budget: at most 4096 hubs and 2 GiB per side; keep the largest
+        size_t cap = (size_t)std::min<long long>(4096, (2LL << 30) / bm_bytes);
+        if (hubs.size() > cap) {
+            std::sort(hubs.begin(), hubs.end(), [&](int a, int b) { return mdeg[a] > mdeg[b]; });
+            hubs.resize(cap);
+            std::sort(hubs.begin(), hubs.end());
+        }
+        g->n_hubs[side] = (int)hubs.size();
+        g->hub_min_deg[side] = min_deg;
+        if (hubs.empty()) continue;
+        // expansion-side descriptors: a copy of the middle rows with the hubs' entries replaced
+        const unsigned long long* d_mrow = (const unsigned long long*)(us ? g->b_row : g->u_row);
+        std::vector<unsigned long long> xrow((size_t)n_mid);
+        BLP_CUDA_TRY(cudaMemcpy(xrow.data(), d_mrow, sizeof(unsigned long long) * (size_t)n_mid,
+                                cudaMemcpyDeviceToHost));
+        for (size_t h = 0; h < hubs.size(); ++h)
+            xrow[hubs[h]] = (1ull << 63) | ((unsigned long long)h << 24) | (unsigned)mdeg[hubs[h]];
+        int* d_nodes = nullptr;
+        const size_t bytes = hubs.size() * (size_t)bm_bytes;
+        BLP_CUDA_TRY(cudaMalloc((void**)&g->xrow[side], sizeof(unsigned long long) * (size_t)n_mid));
+        BLP_CUDA_TRY(cudaMemcpy(g->xrow[side], xrow.data(),
+                                sizeof(unsigned long long) * (size_t)n_mid, cudaMemcpyHostToDevice));
+        BLP_CUDA_TRY(cudaMalloc((void**)&g->hub_bm[side], bytes));
+        BLP_CUDA_TRY(cudaMemset(g->hub_bm[side], 0, bytes));
+        BLP_CUDA_TRY(cudaMalloc((void**)&d_nodes, sizeof(int) * hubs.size()));
+        BLP_CUDA_TRY(cudaMemcpy(d_nodes, hubs.data(), sizeof(int) * hubs.size(),
+                                cudaMemcpyHostToDevice));
+        k_build_hub_bitmaps<<<(int)std::min<size_t>(hubs.size(), 4096), 256>>>(
+            d_nodes, (int)hubs.size(),
+            (const unsigned long long*)(us ? g->b_row : g->u_row), us ? g->b_adj : g->u_adj,
+            words, g->hub_bm[side]);
+        BLP_CUDA_TRY(cudaGetLastError());
+        BLP_CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(d_nodes);
+        g->device_bytes += (int64_t)bytes + (int64_t)sizeof(unsigned long long) * n_mid;
+    }
+    return BLP_OK;
+}
+
 }  // namespace blp
 
 extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, const int32_t* pair_b,
@@ -575,6 +703,8 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     const int* g_deg = us ? g->u_deg : g->b_deg;
     const int* m_deg = us ? g->b_deg : g->u_deg;
     a.m_adjw = us ? g->b_adjw : g->u_adjw;
+    a.m_xrow = g->xrow[side] ? (const unsigned long long*)g->xrow[side] : a.m_row;
+    a.hub_bm = g->hub_bm[side];
     a.n_side = us ? g->n_users : g->n_biz;
     const int n_mid = us ? g->n_biz : g->n_users;
     const int* gx = us ? pair_u : pair_b;
@@ -587,7 +717,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     a.hop2 = hop2_size;
 
     // bitmap must hold bits 0..n_side (the last one is the padding sentinel), 16-byte multiple
-    a.bm_words = (int)((((long long)a.n_side + 1 + 31) / 32 + 3) & ~3LL);
+    a.bm_words = bitmap_words(a.n_side);
     const size_t smem = (size_t)a.bm_words * 4 + sizeof(TileSmem);
     if (smem > (size_t)g->max_smem_optin) {
         char buf[200];

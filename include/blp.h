@@ -59,6 +59,10 @@ typedef struct blp_graph_info_t {
     int64_t device_bytes;     /* HBM held by the handle */
     int32_t device;
     int32_t sm_count;
+    int32_t n_hub_biz;        /* businesses whose user list is also kept as a bitmap (user side) */
+    int32_t n_hub_users;      /* users whose business list is also kept as a bitmap (business side) */
+    int32_t hub_min_biz_degree;
+    int32_t hub_min_user_degree;
 } blp_graph_info_t;
 
 /* Per-launch accounting of the last blp_score_pairs call on a handle (for bench / roofline). */

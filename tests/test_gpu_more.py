@@ -102,6 +102,21 @@ def test_hub_rows_and_big_groups(mods):
     check_against(got, want, pu.size)
 
 
+def test_hub_bitmaps_do_not_change_results(mods, monkeypatch):
+    """Hub lists OR-ed as bitmaps vs every list walked id by id: bit-identical outputs."""
+    graph, synth = mods
+    cfg, eu, eb, pu, pv = synth.make_config('C1', n_pairs=30_000)
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    assert G.info()['n_hub_biz'] > 0 and G.info()['n_hub_users'] > 0
+    with_hubs = G.score_pairs_host(pu, pv, want_hop2=True)
+    monkeypatch.setenv('BLP_HUB_MIN_DEG', '0')          # 0 disables hub selection
+    G2 = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    assert G2.info()['n_hub_biz'] == 0 and G2.info()['n_hub_users'] == 0
+    without = G2.score_pairs_host(pu, pv, want_hop2=True)
+    for k in with_hubs:
+        assert np.array_equal(with_hubs[k], without[k]), k
+
+
 @pytest.mark.timeout(600)
 def test_full_c2_properties(mods):
     """Full BASELINE.json configs[1] size (10M pairs): size-independent properties."""
