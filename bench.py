@@ -126,7 +126,18 @@ def cpu_reference(cfg, eu, eb, pu, pv, n_user_groups, n_biz_groups, procs):
               (s_u, n_user_groups, t_u, s_b, n_biz_groups, t_b, procs))
     _G = None
     _EX = None
-    return rate, sample, {'user_pairs_per_s': s_u / t_u, 'business_pairs_per_s': s_b / t_b}
+    sides = {'user_pairs_per_s': s_u / t_u, 'business_pairs_per_s': s_b / t_b}
+    # for context: the plain-C restatement (oracle/blp_oracle.c), one thread, first 1M pairs
+    try:
+        from oracle import c_oracle
+        m = min(int(pu.size), 1_000_000)
+        t0 = time.perf_counter()
+        c_oracle.score_pair_arrays(cfg['n_users'], cfg['n_biz'], eu, eb, pu[:m], pv[:m])
+        sides['c_port_1thread_pairs_per_s'] = m / (time.perf_counter() - t0)
+        sides['c_port_sample'] = 'first %d pairs, graph build included' % m
+    except Exception as exc:   # the C oracle is optional context, never the headline
+        sides['c_port_error'] = repr(exc)
+    return rate, sample, sides
 
 
 def _cpu_worker_packed(args):

@@ -191,7 +191,7 @@ struct TileSmem {
     int wsum[32];
     int red[32];
     int item_next;
-    int hop2;
+    int hop2cnt;                       // bits turned on during the expansion of this group
     int nhub;
 };
 
@@ -236,14 +236,6 @@ __device__ __forceinline__ int find_list(const TileSmem& ts, int c, int lane) {
     return kb * 8 + __popc(__ballot_sync(kFull, v2 <= c)) - 1;
 }
 
-// The three things done to a streamed id.
-//   OP_SET  plain read-modify-write of the bitmap word.  Concurrent writers of one word can lose
-//           each other's bits (shared-memory atomics cost ~2 cycles per lane and dominated the
-//           first version of this kernel), so a barrier and an OP_FIX sweep follow.
-//   OP_FIX  re-walks the same ids and repairs any lost bit with an atomic (rare).
-//   OP_TEST membership test of the intersection phase.
-enum { OP_SET = 0, OP_FIX = 1, OP_TEST = 2 };
-
 __device__ __forceinline__ uint4 ldg_stream_u(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -252,17 +244,24 @@ __device__ __forceinline__ uint4 ldg_stream_u(const uint4* p) {
     return r;
 }
 
+// The two things done to a streamed id.
+//   OP_SET  expansion: set the id's bit.  A plain read filters ids whose bit is already there
+//           (hub bitmaps and overlapping lists make that the common case); the rest go through
+//           atomicOr, whose return value tells whether THIS thread turned the bit on -- summing
+//           those gives |hop2| exactly, with no separate popcount pass over the bitmap.
+//   OP_TEST membership test of the intersection phase (cnt = hits, acc = weighted hits).
+enum { OP_SET = 0, OP_TEST = 2 };
+
 template <int OP>
 __device__ __forceinline__ void touch(unsigned* bm, int id, unsigned wt, unsigned& cnt,
-                                      unsigned long long& acc) {
+                                      unsigned long long& acc, int n_side) {
     volatile unsigned* w = bm + (id >> 5);
     if (OP == OP_SET) {
         const unsigned bit = 1u << (id & 31);
-        unsigned old = *w;
-        if (!(old & bit)) *w = old | bit;
-    } else if (OP == OP_FIX) {
-        const unsigned bit = 1u << (id & 31);
-        if (!(*w & bit)) atomicOr(const_cast<unsigned*>(w), bit);
+        if (id < n_side && !(*w & bit)) {          // padding sentinels are never set
+            const unsigned old = atomicOr(const_cast<unsigned*>(w), bit);
+            cnt += !(old & bit);
+        }
     } else {
         // branch-free: the weight rides in the stream next to the id, so a hit costs one
         // integer multiply-add (IMAD.WIDE) instead of a divergent 8-byte gather
@@ -274,19 +273,20 @@ __device__ __forceinline__ void touch(unsigned* bm, int id, unsigned wt, unsigne
 
 template <int OP>
 __device__ __forceinline__ void touch4(unsigned* bm, int4 v, uint4 wt, unsigned& cnt,
-                                       unsigned long long& acc) {
-    touch<OP>(bm, v.x, wt.x, cnt, acc);
-    touch<OP>(bm, v.y, wt.y, cnt, acc);
-    touch<OP>(bm, v.z, wt.z, cnt, acc);
-    touch<OP>(bm, v.w, wt.w, cnt, acc);
+                                       unsigned long long& acc, int n_side) {
+    touch<OP>(bm, v.x, wt.x, cnt, acc, n_side);
+    touch<OP>(bm, v.y, wt.y, cnt, acc, n_side);
+    touch<OP>(bm, v.z, wt.z, cnt, acc, n_side);
+    touch<OP>(bm, v.w, wt.w, cnt, acc, n_side);
 }
 
 // Walks the `count` adjacency lists described by ts.row[] (ts.scan[] already holds the chunk
 // prefix of the long ones).  Short lists: 4 lanes per list, 8 lists per warp pass.  Long lists:
 // 512-id chunks dealt round-robin to warps, so a hub list is spread over the whole CTA.
 template <int NT, int OP>
-__device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, TileSmem& ts,
-                                           int count, int lane, int warp) {
+__device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, TileSmem& ts,
+                                               int count, int lane, int warp) {
+    unsigned set_total = 0;   // OP_SET: bits this thread turned on
     constexpr int NW = NT / 32;
     const int4* adj4 = reinterpret_cast<const int4*>(a.m_adj);
     const uint4* adjw4 = reinterpret_cast<const uint4*>(a.m_adjw);
@@ -308,8 +308,9 @@ __device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, Tile
                 const long long at = row_first4(row) + sub;
                 int4 v = ldg_stream(adj4 + at);
                 uint4 wt = OP == OP_TEST ? ldg_stream_u(adjw4 + at) : zero4;
-                touch4<OP>(bm, v, wt, cnt, acc);
+                touch4<OP>(bm, v, wt, cnt, acc, a.n_side);
             }
+            if (OP == OP_SET) set_total += cnt;
             if (OP == OP_TEST) {
                 cnt += __shfl_xor_sync(kFull, cnt, 1);
                 cnt += __shfl_xor_sync(kFull, cnt, 2);
@@ -349,9 +350,10 @@ __device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, Tile
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (32 * k < n) {
-                if (OP == OP_TEST || lane + 32 * k < n) touch4<OP>(bm, v[k], wt[k], cnt, acc);
+                touch4<OP>(bm, v[k], wt[k], cnt, acc, a.n_side);   // sentinels: no-ops
             }
         }
+        if (OP == OP_SET) set_total += cnt;
         if (OP == OP_TEST) {
             const bool single = ((row_deg(row) + 3) >> 2) <= kChunkV4;   // whole list in this chunk
             if (single || __any_sync(kFull, cnt > 0)) {
@@ -370,6 +372,7 @@ __device__ __forceinline__ void sweep_tile(const SideArgs& a, unsigned* bm, Tile
             }
         }
     }
+    return set_total;
 }
 
 __device__ __forceinline__ int long_chunks(unsigned long long row) {
@@ -411,6 +414,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
     if (tid == 0) {
         ts.item_next = atomicAdd(a.work_counter, 1);
         ts.nhub = 0;
+        ts.hop2cnt = 0;
     }
     for (;;) {
         __syncthreads();   // previous item fully retired; ts.item_next published
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 if (a.pa) a.pa[idx] = 0;
                 if (a.hop2) a.hop2[idx] = 0;
             }
-            if (tid == 0) ts.item_next = claimed;
+            if (tid == 0) ts.item_next = claimed;   // hop2cnt untouched: still 0
             continue;
         }
 
@@ -446,7 +450,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         // ---- phases 0+1: two-hop expansion, hop2(x) = U N(m) over m in N(x).
         // Hub lists arrive as precomputed bitmaps and are OR-ed with 128-bit loads by the thread
         // that owns the word (for the first tile this pass doubles as the clear); every other
-        // list is walked id by id (OP_SET, then OP_FIX after a barrier).
+        // list is walked id by id (OP_SET).  Both count the bits they turn on.
         for (int tb = 0; tb < xdeg; tb += kTile) {
             const int count = min(kTile, xdeg - tb);
             int nch = 0;
@@ -461,6 +465,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             }
             tile_scan<NT>(ts, nch, tid);
             BLP_TICK(1);
+            int newbits = 0;
             {
                 const int nhub = ts.nhub;
                 uint4* b4 = reinterpret_cast<uint4*>(bm);
@@ -477,6 +482,8 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                         for (int k = 0; k < 4; ++k) {
                             const int i = i0 + k * NT;
                             acc[k] = (tb == 0 || i >= n4) ? make_uint4(0u, 0u, 0u, 0u) : b4[i];
+                            newbits -= __popc(acc[k].x) + __popc(acc[k].y) + __popc(acc[k].z) +
+                                       __popc(acc[k].w);
                         }
                         for (int h = 0; h < nhub; ++h) {
                             const uint4* src = h4 + (size_t)ts.hub[h] * n4;
@@ -497,6 +504,8 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const int i = i0 + k * NT;
+                            newbits += __popc(acc[k].x) + __popc(acc[k].y) + __popc(acc[k].z) +
+                                       __popc(acc[k].w);
                             if (i < n4) b4[i] = acc[k];
                         }
                     }
@@ -505,43 +514,16 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             __syncthreads();
             if (tid == 0) ts.nhub = 0;
             BLP_TICK(2);
-            sweep_tile<NT, OP_SET>(a, bm, ts, count, lane, warp);
+            newbits += (int)sweep_tile<NT, OP_SET>(a, bm, ts, count, lane, warp);
+            newbits = __reduce_add_sync(kFull, newbits);
+            if (lane == 0 && newbits != 0) atomicAdd(&ts.hop2cnt, newbits);
             __syncthreads();
             BLP_TICK(3);
-            sweep_tile<NT, OP_FIX>(a, bm, ts, count, lane, warp);
-            __syncthreads();
-            BLP_TICK(4);
         }
 
-        // ---- phase 2: |hop2(x)| = popcount minus x itself and the padding sentinel
-        {
-            int c = 0;
-            {
-                const uint4* b4 = reinterpret_cast<const uint4*>(bm);
-                const int n4 = a.bm_words >> 2;
-#pragma unroll 4
-                for (int i = tid; i < n4; i += NT) {
-                    uint4 q = b4[i];
-                    c += __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
-                }
-            }
-            c = __reduce_add_sync(kFull, c);
-            int adj = 0;
-            if (tid == 0) {
-                adj = ((bm[x >> 5] >> (x & 31)) & 1) + ((bm[a.n_side >> 5] >> (a.n_side & 31)) & 1);
-            }
-            if (lane == 0) ts.red[warp] = c;
-            __syncthreads();
-            if (tid == 0) {
-                int tot = 0;
-                for (int w = 0; w < NW; ++w) tot += ts.red[w];
-                ts.hop2 = tot - adj;
-                bm[x >> 5] &= ~(1u << (x & 31));
-                bm[a.n_side >> 5] &= ~(1u << (a.n_side & 31));
-            }
-            __syncthreads();
-        }
-        const int hop2 = ts.hop2;
+        // ---- phase 2: x itself is in every N(m), so its bit is always on: |hop2(x)| = bits - 1
+        const int hop2 = ts.hop2cnt - 1;
+        if (tid == 0) bm[x >> 5] &= ~(1u << (x & 31));   // ordered before the tests by tile_scan
         BLP_TICK(5);
 
         // ---- phase 3: every pair (x, y) of the group: stream N(y), test, count, weigh
@@ -577,7 +559,10 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             __syncthreads();
             BLP_TICK(8);
         }
-        if (tid == 0) ts.item_next = claimed;
+        if (tid == 0) {
+            ts.item_next = claimed;
+            ts.hop2cnt = 0;
+        }
     }
 }
 

@@ -15,8 +15,8 @@ cfg, eu, eb, pu, pv = synth.make_config(cfgname)
 G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, device=0)
 lib = L.load()
 du, dv = torch.from_numpy(pu).cuda(), torch.from_numpy(pv).cuda()
-names = ['fetch(top barrier..item)', 'exp tile load+scan', 'clear / hub-bitmap OR', 'SET sweep', 'FIX sweep',
-         'popcount', 'pair tile load+scan', 'TEST sweep', 'epilogue']
+names = ['fetch(top barrier..item)', 'exp tile load+scan', 'clear / hub-bitmap OR', 'SET sweep', '-',
+         'hop2 finalize', 'pair tile load+scan', 'TEST sweep', 'epilogue']
 buf = (ctypes.c_ulonglong * 16)()
 for side in (0, 1):
     G.score_side(side, du, dv, want_pa=(side == 0))
