@@ -197,7 +197,7 @@ class ClockSampler(object):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--config', default='C2')
     ap.add_argument('--pairs', type=int, default=None, help='pairs per GPU (default: config)')
@@ -227,16 +227,19 @@ def main():
                 (a.config, cfg['n_users'], cfg['n_biz'], cfg['n_reviews'], per_gpu, cfg['k']))
     config = {'workload': workload, 'name': a.config, 'pairs_per_gpu': per_gpu,
               'outputs_per_pair': 9, 'l2': 'L2 flushed (256 MiB write) before every timed step',
-              'sharding': 'adjacency replicated, contiguous user-aligned pair shards'}
+              'sharding': 'adjacency replicated per GPU; every rank scores its own shard of '
+                          'pairs_per_gpu pairs (drawn like the N=1 workload, seed 1+rank); no '
+                          'collective in the timed region'}
     cores = len(os.sched_getaffinity(0))
 
-    # every rank generates the same graph; its own pair shard
+    # every rank generates the same graph and its own pair shard.  Weak scaling: each shard is
+    # drawn exactly like the N=1 workload (same K, same sampler, seed 1+rank), so the per-GPU work
+    # does not change shape with N; rank 0's shard IS the N=1 workload.
     eu, eb = synth.make_graph(seed=0, **cfg)
     deg = synth.degrees(cfg['n_users'], cfg['n_biz'], eu, eb)
     pcfg = dict(cfg)
-    pcfg['n_pairs'] = per_gpu * world
-    pu, pv = synth.make_pairs(edge_u=eu, edge_b=eb, seed=1, rank=rank, world=world, deg=deg,
-                              **pcfg)
+    pcfg['n_pairs'] = per_gpu
+    pu, pv = synth.make_pairs(edge_u=eu, edge_b=eb, seed=1 + rank, deg=deg, **pcfg)
 
     ug = a.cpu_user_groups or 600 * cores
     bg = a.cpu_biz_groups or 250 * cores
