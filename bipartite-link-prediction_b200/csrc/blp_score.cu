@@ -47,6 +47,14 @@ struct SideArgs {
     // entry is  1<<63 | bitmap slot << 24 | degree  (one gather tells list from bitmap)
     const unsigned long long* __restrict__ m_xrow;
     const unsigned* __restrict__ hub_bm;
+    int hub_words;                        // words per hub bitmap (whole id universe)
+    // id-range passes: when the bitmap of the whole universe does not fit (or is not wanted) in
+    // shared memory the group is processed n_ranges times, pass r covering ids
+    // [r*range_bits, (r+1)*range_bits); partial cn / aa wait in scratch (grouped order)
+    int range_bits;
+    int n_ranges;
+    int* acc_cn;
+    unsigned long long* acc_aa;
     // grouping
     const long long* __restrict__ grp_off;  // [n_side + 2]; key n_side = "not in graph"
     const int* __restrict__ item_key;       // non-empty group keys
@@ -252,9 +260,27 @@ __device__ __forceinline__ uint4 ldg_stream_u(const uint4* p) {
 //   OP_TEST membership test of the intersection phase (cnt = hits, acc = weighted hits).
 enum { OP_SET = 0, OP_TEST = 2 };
 
-template <int OP>
+template <int OP, bool RANGED>
 __device__ __forceinline__ void touch(unsigned* bm, int id, unsigned wt, unsigned& cnt,
-                                      unsigned long long& acc, int n_side) {
+                                      unsigned long long& acc, int n_side, int lo, int range_bits) {
+    if (RANGED) {
+        // only ids of the current range [lo, lo + range_bits) have a bit in shared memory
+        const unsigned rel = (unsigned)(id - lo);
+        const bool in = rel < (unsigned)range_bits;
+        volatile unsigned* w = bm + (rel >> 5);
+        if (OP == OP_SET) {
+            const unsigned bit = 1u << (rel & 31);
+            if (in && id < n_side && !(*w & bit)) {
+                const unsigned old = atomicOr(const_cast<unsigned*>(w), bit);
+                cnt += !(old & bit);
+            }
+        } else if (in) {
+            const unsigned hit = (*w >> (rel & 31)) & 1u;
+            cnt += hit;
+            acc += (unsigned long long)hit * (unsigned long long)wt;
+        }
+        return;
+    }
     volatile unsigned* w = bm + (id >> 5);
     if (OP == OP_SET) {
         const unsigned bit = 1u << (id & 31);
@@ -271,21 +297,21 @@ __device__ __forceinline__ void touch(unsigned* bm, int id, unsigned wt, unsigne
     }
 }
 
-template <int OP>
+template <int OP, bool RANGED>
 __device__ __forceinline__ void touch4(unsigned* bm, int4 v, uint4 wt, unsigned& cnt,
-                                       unsigned long long& acc, int n_side) {
-    touch<OP>(bm, v.x, wt.x, cnt, acc, n_side);
-    touch<OP>(bm, v.y, wt.y, cnt, acc, n_side);
-    touch<OP>(bm, v.z, wt.z, cnt, acc, n_side);
-    touch<OP>(bm, v.w, wt.w, cnt, acc, n_side);
+                                       unsigned long long& acc, int n_side, int lo, int range_bits) {
+    touch<OP, RANGED>(bm, v.x, wt.x, cnt, acc, n_side, lo, range_bits);
+    touch<OP, RANGED>(bm, v.y, wt.y, cnt, acc, n_side, lo, range_bits);
+    touch<OP, RANGED>(bm, v.z, wt.z, cnt, acc, n_side, lo, range_bits);
+    touch<OP, RANGED>(bm, v.w, wt.w, cnt, acc, n_side, lo, range_bits);
 }
 
 // Walks the `count` adjacency lists described by ts.row[] (ts.scan[] already holds the chunk
 // prefix of the long ones).  Short lists: 4 lanes per list, 8 lists per warp pass.  Long lists:
 // 512-id chunks dealt round-robin to warps, so a hub list is spread over the whole CTA.
-template <int NT, int OP>
+template <int NT, int OP, bool RANGED>
 __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, TileSmem& ts,
-                                               int count, int lane, int warp) {
+                                               int count, int lane, int warp, int lo) {
     unsigned set_total = 0;   // OP_SET: bits this thread turned on
     constexpr int NW = NT / 32;
     const int4* adj4 = reinterpret_cast<const int4*>(a.m_adj);
@@ -308,7 +334,7 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
                 const long long at = row_first4(row) + sub;
                 int4 v = ldg_stream(adj4 + at);
                 uint4 wt = OP == OP_TEST ? ldg_stream_u(adjw4 + at) : zero4;
-                touch4<OP>(bm, v, wt, cnt, acc, a.n_side);
+                touch4<OP, RANGED>(bm, v, wt, cnt, acc, a.n_side, lo, a.range_bits);
             }
             if (OP == OP_SET) set_total += cnt;
             if (OP == OP_TEST) {
@@ -350,7 +376,7 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (32 * k < n) {
-                touch4<OP>(bm, v[k], wt[k], cnt, acc, a.n_side);   // sentinels: no-ops
+                touch4<OP, RANGED>(bm, v[k], wt[k], cnt, acc, a.n_side, lo, a.range_bits);
             }
         }
         if (OP == OP_SET) set_total += cnt;
@@ -398,7 +424,7 @@ __device__ unsigned long long g_phase_cycles[16];
 #define BLP_THREADS_PER_SM 1024
 #endif
 
-template <int NT>
+template <int NT, bool RANGED>
 __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREADS_PER_SM / NT) : 1)
     k_score_side(SideArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -447,6 +473,9 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         const int xdeg = row_deg(xrow);
         const int* xadj = a.g_adj + row_first4(xrow) * 4;
 
+        const int n_ranges = RANGED ? a.n_ranges : 1;
+        for (int pass = 0; pass < n_ranges; ++pass) {
+        const int lo = RANGED ? pass * a.range_bits : 0;
         // ---- phases 0+1: two-hop expansion, hop2(x) = U N(m) over m in N(x).
         // Hub lists arrive as precomputed bitmaps and are OR-ed with 128-bit loads by the thread
         // that owns the word (for the first tile this pass doubles as the clear); every other
@@ -485,13 +514,15 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                             newbits -= __popc(acc[k].x) + __popc(acc[k].y) + __popc(acc[k].z) +
                                        __popc(acc[k].w);
                         }
+                        const int hub4 = a.hub_words >> 2, lo4 = lo >> 7;
                         for (int h = 0; h < nhub; ++h) {
-                            const uint4* src = h4 + (size_t)ts.hub[h] * n4;
+                            const uint4* src = h4 + (size_t)ts.hub[h] * hub4 + lo4;
                             uint4 q[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const int i = i0 + k * NT;
-                                q[k] = i < n4 ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+                                q[k] = (i < n4 && lo4 + i < hub4) ? __ldg(src + i)
+                                                                  : make_uint4(0u, 0u, 0u, 0u);
                             }
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
@@ -514,7 +545,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             __syncthreads();
             if (tid == 0) ts.nhub = 0;
             BLP_TICK(2);
-            newbits += (int)sweep_tile<NT, OP_SET>(a, bm, ts, count, lane, warp);
+            newbits += (int)sweep_tile<NT, OP_SET, RANGED>(a, bm, ts, count, lane, warp, lo);
             newbits = __reduce_add_sync(kFull, newbits);
             if (lane == 0 && newbits != 0) atomicAdd(&ts.hop2cnt, newbits);
             __syncthreads();
@@ -522,8 +553,12 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         }
 
         // ---- phase 2: x itself is in every N(m), so its bit is always on: |hop2(x)| = bits - 1
+        // (with id ranges the count is complete once the last pass has expanded)
         const int hop2 = ts.hop2cnt - 1;
-        if (tid == 0) bm[x >> 5] &= ~(1u << (x & 31));   // ordered before the tests by tile_scan
+        if (tid == 0) {   // ordered before the tests by tile_scan's barriers
+            const unsigned rel = (unsigned)(x - lo);
+            if (!RANGED || rel < (unsigned)a.range_bits) bm[rel >> 5] &= ~(1u << (rel & 31));
+        }
         BLP_TICK(5);
 
         // ---- phase 3: every pair (x, y) of the group: stream N(y), test, count, weigh
@@ -540,11 +575,24 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             }
             tile_scan<NT>(ts, nch, tid);
             BLP_TICK(6);
-            sweep_tile<NT, OP_TEST>(a, bm, ts, count, lane, warp);
+            sweep_tile<NT, OP_TEST, RANGED>(a, bm, ts, count, lane, warp, lo);
             __syncthreads();
             BLP_TICK(7);
             // epilogue: one thread per pair of the tile
-            if (tid < count) {
+            bool final_pass = true;
+            if (RANGED && tid < count) {
+                // partial sums of earlier ranges wait in scratch; only the last pass emits
+                if (pass > 0) {
+                    ts.cn[tid] += a.acc_cn[tb + tid];
+                    ts.aa[tid] += a.acc_aa[tb + tid];
+                }
+                final_pass = pass == n_ranges - 1;
+                if (!final_pass) {
+                    a.acc_cn[tb + tid] = ts.cn[tid];
+                    a.acc_aa[tb + tid] = ts.aa[tid];
+                }
+            }
+            if (tid < count && final_pass) {
                 int idx = ts.idx[tid];
                 int c = ts.cn[tid];
                 int pdeg = row_deg(ts.row[tid]);
@@ -559,6 +607,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             __syncthreads();
             BLP_TICK(8);
         }
+        }   // id-range passes
         if (tid == 0) {
             ts.item_next = claimed;
             ts.hop2cnt = 0;
@@ -566,20 +615,21 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
     }
 }
 
-template <int NT>
+template <int NT, bool RANGED>
 static int launch_side(const SideArgs& a, int grid, size_t smem, cudaStream_t st) {
-    BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_side<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    k_score_side<NT><<<grid, NT, smem, st>>>(a);
+    BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_side<NT, RANGED>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_score_side<NT, RANGED><<<grid, NT, smem, st>>>(a);
     BLP_CUDA_TRY(cudaGetLastError());
     return BLP_OK;
 }
 
-template <int NT>
+template <int NT, bool RANGED>
 static int occupancy(size_t smem, int* ctas_per_sm) {
-    BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_side<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    BLP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_score_side<NT>, NT, smem));
+    BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_side<NT, RANGED>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BLP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm,
+                                                               k_score_side<NT, RANGED>, NT, smem));
     return BLP_OK;
 }
 
@@ -701,16 +751,27 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     a.pa = (long long*)pa;
     a.hop2 = hop2_size;
 
-    // bitmap must hold bits 0..n_side (the last one is the padding sentinel), 16-byte multiple
-    a.bm_words = bitmap_words(a.n_side);
+    // The bitmap must hold bits 0..n_side (the last one is the padding sentinel).  When that does
+    // not fit in one CTA's shared memory the id universe is cut into equal ranges and every group
+    // is processed once per range (BLP_RANGES forces a count, for tuning).
+    const int full_words = bitmap_words(a.n_side);
+    a.hub_words = full_words;
+    const long long cap_words =
+        (((long long)g->max_smem_optin - (long long)sizeof(TileSmem) - 256) / 4) & ~3LL;
+    int n_ranges = (int)((full_words + cap_words - 1) / cap_words);
+    if (const char* e = getenv("BLP_RANGES")) n_ranges = std::max(n_ranges, atoi(e));
+    int range_words = full_words;
+    if (n_ranges > 1) {
+        range_words = (int)((((long long)full_words + n_ranges - 1) / n_ranges + 3) & ~3LL);
+        n_ranges = (full_words + range_words - 1) / range_words;
+    }
+    const bool ranged = n_ranges > 1;
+    a.bm_words = range_words;
+    a.range_bits = range_words * 32;
+    a.n_ranges = n_ranges;
     const size_t smem = (size_t)a.bm_words * 4 + sizeof(TileSmem);
     if (smem > (size_t)g->max_smem_optin) {
-        char buf[200];
-        snprintf(buf, sizeof(buf),
-                 "blp_score_pairs: hop-2 bitmap of %d nodes needs %zu B of shared memory, device "
-                 "offers %d B per CTA (id-range passes not built yet)",
-                 a.n_side, smem, g->max_smem_optin);
-        set_error(buf);
+        set_error("blp_score_pairs: internal error sizing the shared-memory bitmap");
         return BLP_ERR_UNSUPPORTED;
     }
 
@@ -728,6 +789,10 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     BLP_CUDA_TRY(cudaMallocAsync((void**)&scalars, sizeof(int) * 2, st));
     BLP_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
     BLP_CUDA_TRY(cudaMemsetAsync(scalars, 0, sizeof(int) * 2, st));
+    if (ranged) {
+        BLP_CUDA_TRY(cudaMallocAsync((void**)&a.acc_cn, sizeof(int) * (size_t)n, st));
+        BLP_CUDA_TRY(cudaMallocAsync((void**)&a.acc_aa, sizeof(unsigned long long) * (size_t)n, st));
+    }
 
     BLP_CUDA_TRY(cudaEventRecord(g->ev[side][0], st));
     const int gblocks = (int)std::min<long long>((n + 255) / 256, (long long)g->sm_count * 16);
@@ -753,46 +818,38 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     const size_t budget = (size_t)g->max_smem_optin;
     const char* nt_env = getenv("BLP_NT");   // tuning override
     const int nt_force = nt_env ? atoi(nt_env) : 0;
-    if (nt_force == 128 && kTile <= 128) {
-        nt = 128;
-        rc = occupancy<128>(smem, &per_sm);
-    } else if (nt_force == 384) {
-        nt = 384;
-        rc = occupancy<384>(smem, &per_sm);
-    } else if (nt_force == 512) {
-        nt = 512;
-        rc = occupancy<512>(smem, &per_sm);
-    } else if (nt_force == 1024) {
-        nt = 1024;
-        rc = occupancy<1024>(smem, &per_sm);
-    } else if (smem * 4 + 4096 <= budget) {
-        nt = 256;
-        rc = occupancy<256>(smem, &per_sm);
-    } else if (smem * 2 + 2048 <= budget) {
-        nt = 512;
-        rc = occupancy<512>(smem, &per_sm);
+    if (nt_force == 256 || nt_force == 512 || nt_force == 1024) nt = nt_force;
+    else if (smem * 4 + 4096 <= budget) nt = 256;
+    else if (smem * 2 + 2048 <= budget) nt = 512;
+    else nt = 1024;
+#define BLP_DISPATCH(NTV, RV)                                               \
+    do {                                                                    \
+        rc = occupancy<NTV, RV>(smem, &per_sm);                             \
+        if (rc == BLP_OK && per_sm < 1) {                                   \
+            set_error("blp_score_pairs: scoring kernel does not fit on an SM"); \
+            rc = BLP_ERR_UNSUPPORTED;                                       \
+        }                                                                   \
+        if (rc == BLP_OK) rc = launch_side<NTV, RV>(a, per_sm * g->sm_count, smem, st); \
+    } while (0)
+    if (nt == 256) {
+        if (ranged) BLP_DISPATCH(256, true); else BLP_DISPATCH(256, false);
+    } else if (nt == 512) {
+        if (ranged) BLP_DISPATCH(512, true); else BLP_DISPATCH(512, false);
     } else {
-        nt = 1024;
-        rc = occupancy<1024>(smem, &per_sm);
+        if (ranged) BLP_DISPATCH(1024, true); else BLP_DISPATCH(1024, false);
     }
-    if (rc == BLP_OK && per_sm < 1) {
-        set_error("blp_score_pairs: scoring kernel does not fit on an SM");
-        rc = BLP_ERR_UNSUPPORTED;
-    }
+#undef BLP_DISPATCH
     if (rc == BLP_OK) {
-        const int grid = per_sm * g->sm_count;
-        if (nt == 128) rc = launch_side<128>(a, grid, smem, st);
-        else if (nt == 256) rc = launch_side<256>(a, grid, smem, st);
-        else if (nt == 384) rc = launch_side<384>(a, grid, smem, st);
-        else if (nt == 512) rc = launch_side<512>(a, grid, smem, st);
-        else rc = launch_side<1024>(a, grid, smem, st);
-        if (rc == BLP_OK && cudaEventRecord(g->ev[side][2], st) == cudaSuccess)
-            g->ev_recorded[side] = true;
-        stats.ctas = grid;
+        if (cudaEventRecord(g->ev[side][2], st) == cudaSuccess) g->ev_recorded[side] = true;
+        stats.ctas = per_sm * g->sm_count;
         stats.threads_per_cta = nt;
         stats.smem_bytes = (int)smem;
         stats.kernel_launches = 4;
-        stats.range_passes = 1;
+        stats.range_passes = n_ranges;
+    }
+    if (ranged) {
+        cudaFreeAsync(a.acc_cn, st);
+        cudaFreeAsync(a.acc_aa, st);
     }
     cudaFreeAsync(cnt, st);
     cudaFreeAsync(cursor, st);

@@ -117,6 +117,38 @@ def test_hub_bitmaps_do_not_change_results(mods, monkeypatch):
         assert np.array_equal(with_hubs[k], without[k]), k
 
 
+def test_id_range_passes_do_not_change_results(mods, monkeypatch):
+    """Bitmap cut into id ranges (several passes per group) vs one pass: bit-identical."""
+    graph, synth = mods
+    lib = pkg('_lib')
+    cfg, eu, eb, pu, pv = synth.make_config('C1', n_pairs=30_000)
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    one = G.score_pairs_host(pu, pv, want_hop2=True)
+    assert G.score_stats(lib.SIDE_USER)['range_passes'] == 1
+    for r in ('2', '5'):
+        monkeypatch.setenv('BLP_RANGES', r)
+        many = G.score_pairs_host(pu, pv, want_hop2=True)
+        assert G.score_stats(lib.SIDE_USER)['range_passes'] == int(r)
+        for k in one:
+            assert np.array_equal(one[k], many[k]), (r, k)
+
+
+def test_universe_larger_than_shared_memory(mods):
+    """2.5M users: the hop-2 bitmap (312 KB) exceeds one CTA's shared memory -> automatic ranges."""
+    from oracle import c_oracle
+    graph, synth = mods
+    lib = pkg('_lib')
+    n_users, n_biz = 2_500_000, 3000
+    eu, eb = synth.make_graph(n_users, n_biz, 400_000, seed=5, shift_u=50.0, shift_b=5.0)
+    pu, pv = synth.make_pairs(n_users, n_biz, eu, eb, 20_000, k=8, seed=6)
+    G = graph.BipartiteGraph(n_users, n_biz, eu, eb)
+    got = G.score_pairs_host(pu, pv)
+    assert G.score_stats(lib.SIDE_USER)['range_passes'] >= 2
+    assert G.score_stats(lib.SIDE_BUSINESS)['range_passes'] == 1
+    want = c_oracle.score_pair_arrays(n_users, n_biz, eu, eb, pu, pv)
+    check_against(got, want, pu.size)
+
+
 @pytest.mark.timeout(600)
 def test_full_c2_properties(mods):
     """Full BASELINE.json configs[1] size (10M pairs): size-independent properties."""
