@@ -363,20 +363,24 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
         const int off4 = (c - ts.scan[j]) * kChunkV4;
         const int n = min(kChunkV4, ((row_deg(row) + 3) >> 2) - off4);
         const long long at = row_first4(row) + off4;
-        int4 v[4];
-        uint4 wt[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int i = lane + 32 * k;
-            v[k] = i < n ? ldg_stream(adj4 + at + i) : sent4;
-            wt[k] = (OP == OP_TEST && i < n) ? ldg_stream_u(adjw4 + at + i) : zero4;
-        }
         unsigned cnt = 0;
         unsigned long long acc = 0ull;
+        // two halves of 256 ids: four 128-bit loads in flight per lane, half the registers
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (32 * k < n) {
-                touch4<OP, RANGED>(bm, v[k], wt[k], cnt, acc, a.n_side, lo, a.range_bits);
+        for (int half = 0; half < 2; ++half) {
+            if (64 * half < n) {
+                int4 v[2];
+                uint4 wt[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int i = lane + 32 * (2 * half + k);
+                    v[k] = i < n ? ldg_stream(adj4 + at + i) : sent4;
+                    wt[k] = (OP == OP_TEST && i < n) ? ldg_stream_u(adjw4 + at + i) : zero4;
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    if (32 * (2 * half + k) < n)
+                        touch4<OP, RANGED>(bm, v[k], wt[k], cnt, acc, a.n_side, lo, a.range_bits);
             }
         }
         if (OP == OP_SET) set_total += cnt;
@@ -424,6 +428,31 @@ __device__ unsigned long long g_phase_cycles[16];
 #define BLP_THREADS_PER_SM 1024
 #endif
 
+// Descriptor of one work item (group) as the kernel carries it in registers.  The uniform part
+// of the chain  item -> node -> (pair range, row)  is fetched for the NEXT group in two stages
+// spread over the current group's phases, so it is off the critical path when the group starts;
+// the first pair tile's gathers are issued at group start and parked in shared memory while the
+// expansion runs.
+struct GroupRegs {
+    int item;                   // index into item_key, >= n_items when there is no group
+    int x;                      // grouping node; n_side = the "not in graph" bucket
+    int p0, p1;                 // pair range of the group in grouped order
+    unsigned long long xrow;    // row descriptor of x
+};
+
+__device__ __forceinline__ void stage1(const SideArgs& a, GroupRegs& g, int n_items) {
+    g.x = g.item < n_items ? a.item_key[g.item] : a.n_side + 1;
+}
+__device__ __forceinline__ void stage2(const SideArgs& a, GroupRegs& g) {
+    g.p0 = g.p1 = 0;
+    g.xrow = 0ull;
+    if (g.x <= a.n_side) {
+        g.p0 = (int)a.grp_off[g.x];
+        g.p1 = (int)a.grp_off[g.x + 1];
+        if (g.x < a.n_side) g.xrow = a.g_row[g.x];
+    }
+}
+
 template <int NT, bool RANGED>
 __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREADS_PER_SM / NT) : 1)
     k_score_side(SideArgs a) {
@@ -431,7 +460,6 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
     unsigned* bm = reinterpret_cast<unsigned*>(smem_raw);
     TileSmem& ts = *reinterpret_cast<TileSmem*>(smem_raw + (size_t)a.bm_words * 4);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NT / 32;
     const int n_items = *a.n_items;
 
 #ifdef BLP_PHASE_TIMING
@@ -442,17 +470,20 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         ts.nhub = 0;
         ts.hop2cnt = 0;
     }
-    for (;;) {
-        __syncthreads();   // previous item fully retired; ts.item_next published
+    __syncthreads();
+    GroupRegs cur;
+    cur.item = ts.item_next;
+    stage1(a, cur, n_items);
+    stage2(a, cur);
+
+    while (cur.item < n_items) {
         BLP_TICK(0);
-        const int item = ts.item_next;
-        __syncthreads();
-        if (item >= n_items) break;
-        // claim the next item now; its latency hides behind this group's work
+        // claim the next item now; its descriptor is fetched in stages below
         int claimed = 0;
         if (tid == 0) claimed = atomicAdd(a.work_counter, 1);
-        const int x = a.item_key[item];
-        const long long p0 = a.grp_off[x], p1 = a.grp_off[x + 1];
+        GroupRegs nxt;
+        const int x = cur.x;
+        const long long p0 = cur.p0, p1 = cur.p1;
 
         if (x >= a.n_side) {
             // pairs with an id that is not in the graph: every score is the literal 0
@@ -465,13 +496,27 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 if (a.pa) a.pa[idx] = 0;
                 if (a.hop2) a.hop2[idx] = 0;
             }
-            if (tid == 0) ts.item_next = claimed;   // hop2cnt untouched: still 0
+            __syncthreads();                       // everyone is past reading ts.item_next
+            if (tid == 0) ts.item_next = claimed;
+            __syncthreads();
+            nxt.item = ts.item_next;
+            stage1(a, nxt, n_items);
+            stage2(a, nxt);
+            cur = nxt;
             continue;
         }
 
-        const unsigned long long xrow = a.g_row[x];
+        const unsigned long long xrow = cur.xrow;
         const int xdeg = row_deg(xrow);
         const int* xadj = a.g_adj + row_first4(xrow) * 4;
+        if (tid == 0) ts.item_next = claimed;      // published by the first barrier below
+        // gathers of the first pair tile: issued now, parked in shared memory after the hub pass
+        unsigned long long park_row = 0ull;
+        int park_idx = 0;
+        if (tid < kTile && p0 + tid < p1) {
+            park_row = a.m_row[a.gpartner[p0 + tid]];
+            park_idx = a.perm[p0 + tid];
+        }
 
         const int n_ranges = RANGED ? a.n_ranges : 1;
         for (int pass = 0; pass < n_ranges; ++pass) {
@@ -493,6 +538,10 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 nch = long_chunks(row);
             }
             tile_scan<NT>(ts, nch, tid);
+            if (pass == 0 && tb == 0) {            // stage 1 of the next group's descriptor
+                nxt.item = ts.item_next;
+                stage1(a, nxt, n_items);
+            }
             BLP_TICK(1);
             int newbits = 0;
             {
@@ -504,46 +553,45 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                     if (tb == 0)
                         for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
                 } else {
-                    // four independent 128-bit loads in flight per thread and hub
-                    for (int i0 = tid; i0 < n4; i0 += 4 * NT) {
-                        uint4 acc[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int i = i0 + k * NT;
-                            acc[k] = (tb == 0 || i >= n4) ? make_uint4(0u, 0u, 0u, 0u) : b4[i];
-                            newbits -= __popc(acc[k].x) + __popc(acc[k].y) + __popc(acc[k].z) +
-                                       __popc(acc[k].w);
-                        }
-                        const int hub4 = a.hub_words >> 2, lo4 = lo >> 7;
+                    // two independent 128-bit loads in flight per thread and hub
+                    const int hub4 = a.hub_words >> 2, lo4 = lo >> 7;
+                    for (int i0 = tid; i0 < n4; i0 += 2 * NT) {
+                        const int i1 = i0 + NT;
+                        const bool ok1 = i1 < n4;
+                        uint4 acc0 = tb == 0 ? make_uint4(0u, 0u, 0u, 0u) : b4[i0];
+                        uint4 acc1 = (tb == 0 || !ok1) ? make_uint4(0u, 0u, 0u, 0u) : b4[i1];
+                        newbits -= __popc(acc0.x) + __popc(acc0.y) + __popc(acc0.z) + __popc(acc0.w) +
+                                   __popc(acc1.x) + __popc(acc1.y) + __popc(acc1.z) + __popc(acc1.w);
                         for (int h = 0; h < nhub; ++h) {
                             const uint4* src = h4 + (size_t)ts.hub[h] * hub4 + lo4;
-                            uint4 q[4];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const int i = i0 + k * NT;
-                                q[k] = (i < n4 && lo4 + i < hub4) ? __ldg(src + i)
-                                                                  : make_uint4(0u, 0u, 0u, 0u);
-                            }
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                acc[k].x |= q[k].x;
-                                acc[k].y |= q[k].y;
-                                acc[k].z |= q[k].z;
-                                acc[k].w |= q[k].w;
-                            }
+                            const uint4 q0 = lo4 + i0 < hub4 ? __ldg(src + i0)
+                                                             : make_uint4(0u, 0u, 0u, 0u);
+                            const uint4 q1 = (ok1 && lo4 + i1 < hub4) ? __ldg(src + i1)
+                                                                      : make_uint4(0u, 0u, 0u, 0u);
+                            acc0.x |= q0.x;
+                            acc0.y |= q0.y;
+                            acc0.z |= q0.z;
+                            acc0.w |= q0.w;
+                            acc1.x |= q1.x;
+                            acc1.y |= q1.y;
+                            acc1.z |= q1.z;
+                            acc1.w |= q1.w;
                         }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int i = i0 + k * NT;
-                            newbits += __popc(acc[k].x) + __popc(acc[k].y) + __popc(acc[k].z) +
-                                       __popc(acc[k].w);
-                            if (i < n4) b4[i] = acc[k];
-                        }
+                        newbits += __popc(acc0.x) + __popc(acc0.y) + __popc(acc0.z) + __popc(acc0.w) +
+                                   __popc(acc1.x) + __popc(acc1.y) + __popc(acc1.z) + __popc(acc1.w);
+                        b4[i0] = acc0;
+                        if (ok1) b4[i1] = acc1;
                     }
                 }
             }
+            if (pass == 0 && tb == 0 && tid < kTile) {
+                // ts.idx / ts.aa are idle until phase 3: the first pair tile waits there
+                ts.idx[tid] = park_idx;
+                ts.aa[tid] = park_row;
+            }
             __syncthreads();
             if (tid == 0) ts.nhub = 0;
+            if (pass == 0 && tb == 0) stage2(a, nxt);
             BLP_TICK(2);
             newbits += (int)sweep_tile<NT, OP_SET, RANGED>(a, bm, ts, count, lane, warp, lo);
             newbits = __reduce_add_sync(kFull, newbits);
@@ -566,9 +614,10 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             const int count = (int)min((long long)kTile, p1 - tb);
             int nch = 0;
             if (tid < count) {
-                unsigned long long row = a.m_row[a.gpartner[tb + tid]];
+                const bool first = tb == p0 && pass == 0;
+                unsigned long long row = first ? ts.aa[tid] : a.m_row[a.gpartner[tb + tid]];
                 ts.row[tid] = row;
-                ts.idx[tid] = a.perm[tb + tid];
+                if (!first) ts.idx[tid] = a.perm[tb + tid];
                 ts.cn[tid] = 0;
                 ts.aa[tid] = 0ull;
                 nch = long_chunks(row);
@@ -608,10 +657,8 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             BLP_TICK(8);
         }
         }   // id-range passes
-        if (tid == 0) {
-            ts.item_next = claimed;
-            ts.hop2cnt = 0;
-        }
+        if (tid == 0) ts.hop2cnt = 0;   // ordered before the next group's counting by its barriers
+        cur = nxt;
     }
 }
 

@@ -312,32 +312,47 @@ class HostSession(object):
         hb[:] = pair_b
         return self.score_pinned(n)
 
-    def score_pinned(self, n):
-        """Score the first n pairs already sitting in the pinned input buffers."""
+    def score_pinned(self, n, user_chunks=4):
+        """Score the first n pairs already sitting in the pinned input buffers.
+
+        Pipeline: H2D of the pair ids; business side over all pairs; then the user side in
+        `user_chunks` contiguous slices, each slice's results copied back on the copy stream
+        while the next slice is being scored -- only the last slice's D2H is exposed.
+        """
         n = int(n)
         if n > self.n_max:
             raise ValueError('pair count %d exceeds the session capacity %d' % (n, self.n_max))
         g, dev = self.g, self.g.device
+        ukeys = [k for k in self.KEYS if not k.startswith('b_')]
+        bkeys = [k for k in self.KEYS if k.startswith('b_')]
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
+            copy = self.copy_stream
             du, db = self.d_u[:n], self.d_b[:n]
             du.copy_(self.h_u[:n], non_blocking=True)
             db.copy_(self.h_b[:n], non_blocking=True)
-            ob = {k[2:]: self.d_out[k][:n] for k in self.KEYS if k.startswith('b_')}
-            ou = {k[2:]: self.d_out[k][:n] for k in self.KEYS if k.startswith('u_')}
-            ou['pa'] = self.d_out['pa'][:n]
+            ob = {k[2:]: self.d_out[k][:n] for k in bkeys}
             g.score_side(_lib.SIDE_BUSINESS, du, db, out=ob)
-            ev_b = torch.cuda.Event()
-            ev_b.record(main)
-            g.score_side(_lib.SIDE_USER, du, db, want_pa=True, out=ou)
-            with torch.cuda.stream(self.copy_stream):
-                self.copy_stream.wait_event(ev_b)
-                for k in self.KEYS:
-                    if k.startswith('b_'):
-                        self.h_out[k][:n].copy_(self.d_out[k][:n], non_blocking=True)
-            for k in self.KEYS:
-                if not k.startswith('b_'):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(copy):
+                copy.wait_event(ev)
+                for k in bkeys:
                     self.h_out[k][:n].copy_(self.d_out[k][:n], non_blocking=True)
-            main.wait_stream(self.copy_stream)
+            chunks = max(1, min(int(user_chunks), n // 65536 or 1))
+            bounds = [(n * c) // chunks for c in range(chunks + 1)]
+            for c in range(chunks):
+                lo, hi = bounds[c], bounds[c + 1]
+                if hi <= lo:
+                    continue
+                ou = {(k[2:] if k.startswith('u_') else k): self.d_out[k][lo:hi] for k in ukeys}
+                g.score_side(_lib.SIDE_USER, du[lo:hi], db[lo:hi], want_pa=True, out=ou)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(copy):
+                    copy.wait_event(ev)
+                    for k in ukeys:
+                        self.h_out[k][lo:hi].copy_(self.d_out[k][lo:hi], non_blocking=True)
+            main.wait_stream(copy)
             main.synchronize()
         return {k: self.h_out[k][:n].numpy() for k in self.KEYS}

@@ -102,6 +102,28 @@ def test_hub_rows_and_big_groups(mods):
     check_against(got, want, pu.size)
 
 
+def test_host_session_matches_plain_path(mods):
+    """The pinned, chunked, overlapped host pipeline returns what the simple path returns."""
+    graph, synth = mods
+    cfg, eu, eb, pu, pv = synth.make_config('C1', n_pairs=100_000)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(pu.size)                 # not grouped by user: chunks cut anywhere
+    pu, pv = pu[perm], pv[perm]
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    want = G.score_pairs_host(pu, pv)
+    sess = G.host_session(pu.size + 10)
+    for chunks in (1, 4):
+        hu, hb = sess.pinned_inputs(pu.size)
+        hu[:] = pu
+        hb[:] = pv
+        got = sess.score_pinned(pu.size, user_chunks=chunks)
+        for k in want:
+            assert np.array_equal(got[k], want[k]), (chunks, k)
+    got = sess.score(pu[:777], pv[:777])
+    for k in want:
+        assert np.array_equal(got[k], want[k][:777]), k
+
+
 def test_hub_bitmaps_do_not_change_results(mods, monkeypatch):
     """Hub lists OR-ed as bitmaps vs every list walked id by id: bit-identical outputs."""
     graph, synth = mods
