@@ -104,30 +104,30 @@ __global__ void k_group_count(const int* __restrict__ gx, const int* __restrict_
     }
 }
 
-// Single-CTA exclusive scan of the group sizes; also compacts the non-empty keys.
+// Single-CTA exclusive scan of the group sizes; also compacts the non-empty keys.  Four keys per
+// thread and iteration (4096 per trip) keep the serial trip count low: 90 trips for 366 k keys.
 __global__ void __launch_bounds__(1024) k_group_scan(const unsigned* __restrict__ cnt, int n_keys,
                                                      long long* __restrict__ grp_off,
                                                      unsigned* __restrict__ cursor,
                                                      int* __restrict__ item_key,
                                                      int* __restrict__ n_items) {
-    __shared__ long long s_sum[32];
+    __shared__ unsigned s_sum[32];
     __shared__ int s_flag[32];
-    __shared__ long long s_base;
-    __shared__ int s_fbase;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        s_base = 0;
-        s_fbase = 0;
-    }
-    __syncthreads();
-    for (int start = 0; start < n_keys; start += 1024) {
-        int i = start + tid;
-        unsigned c = i < n_keys ? cnt[i] : 0u;
-        long long v = c;
-        int f = c > 0;
-        // inclusive warp scans
+    long long base = 0;   // carried identically by every thread
+    int fbase = 0;
+    for (int start = 0; start < n_keys; start += 4096) {
+        const int i0 = start + tid * 4;
+        unsigned c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = i0 + k < n_keys ? cnt[i0 + k] : 0u;
+        unsigned v = c[0] + c[1] + c[2] + c[3];          // a trip holds < 2^32 pairs in total
+        int f = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
+        const unsigned own_v = v;
+        const int own_f = f;
+#pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            long long t = __shfl_up_sync(kFull, v, d);
+            unsigned t = __shfl_up_sync(kFull, v, d);
             int tf = __shfl_up_sync(kFull, f, d);
             if (lane >= d) {
                 v += t;
@@ -139,29 +139,43 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned* __restrict_
             s_flag[warp] = f;
         }
         __syncthreads();
-        long long wb = 0;
-        int fb = 0;
-        for (int w = 0; w < warp; ++w) {
-            wb += s_sum[w];
-            fb += s_flag[w];
+        unsigned wv = s_sum[lane];
+        int wf = s_flag[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned t = __shfl_up_sync(kFull, wv, d);
+            int tf = __shfl_up_sync(kFull, wf, d);
+            if (lane >= d) {
+                wv += t;
+                wf += tf;
+            }
         }
-        long long base = s_base;
-        int fbase = s_fbase;
-        if (i < n_keys) {
-            grp_off[i] = base + wb + v - c;
-            cursor[i] = 0u;
-            if (c > 0) item_key[fbase + fb + f - 1] = i;
+        const unsigned trip_total = __shfl_sync(kFull, wv, 31);
+        const int trip_flags = __shfl_sync(kFull, wf, 31);
+        unsigned wb = __shfl_sync(kFull, wv, max(warp, 1) - 1);
+        int fb = __shfl_sync(kFull, wf, max(warp, 1) - 1);
+        if (warp == 0) {
+            wb = 0;
+            fb = 0;
         }
-        __syncthreads();
-        if (tid == 1023) {
-            s_base = base + wb + v;
-            s_fbase = fbase + fb + f;
+        long long off = base + wb + (v - own_v);          // exclusive prefix of this thread
+        int slot = fbase + fb + (f - own_f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < n_keys) {
+                grp_off[i0 + k] = off;
+                cursor[i0 + k] = 0u;
+                if (c[k] > 0) item_key[slot++] = i0 + k;
+                off += c[k];
+            }
         }
+        base += trip_total;
+        fbase += trip_flags;
         __syncthreads();
     }
     if (tid == 0) {
-        grp_off[n_keys] = s_base;
-        *n_items = s_fbase;
+        grp_off[n_keys] = base;
+        *n_items = fbase;
     }
 }
 
@@ -300,6 +314,27 @@ __device__ __forceinline__ void touch(unsigned* bm, int id, unsigned wt, unsigne
 template <int OP, bool RANGED>
 __device__ __forceinline__ void touch4(unsigned* bm, int4 v, uint4 wt, unsigned& cnt,
                                        unsigned long long& acc, int n_side, int lo, int range_bits) {
+    if (OP == OP_SET) {
+        // four probes first, then the atomics that are still needed, all in flight together
+        const int id[4] = {v.x, v.y, v.z, v.w};
+        unsigned rel[4], bit[4], old[4];
+        bool need[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            rel[k] = RANGED ? (unsigned)(id[k] - lo) : (unsigned)id[k];
+            bit[k] = 1u << (rel[k] & 31);
+            need[k] = id[k] < n_side && (!RANGED || rel[k] < (unsigned)range_bits);
+            old[k] = need[k] ? *(volatile unsigned*)(bm + (rel[k] >> 5)) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            need[k] = need[k] && !(old[k] & bit[k]);
+            if (need[k]) old[k] = atomicOr(bm + (rel[k] >> 5), bit[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cnt += need[k] && !(old[k] & bit[k]);
+        return;
+    }
     touch<OP, RANGED>(bm, v.x, wt.x, cnt, acc, n_side, lo, range_bits);
     touch<OP, RANGED>(bm, v.y, wt.y, cnt, acc, n_side, lo, range_bits);
     touch<OP, RANGED>(bm, v.z, wt.z, cnt, acc, n_side, lo, range_bits);
@@ -353,11 +388,15 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
     }
     // ---- long lists
     const int total = ts.scan[kTile];
-    for (;;) {
-        int c = 0;
+    int c = 0;
+    if (total > 0) {
         if (lane == 0) c = atomicAdd(&ts.next_chunk[OP], 1);
         c = __shfl_sync(kFull, c, 0);
-        if (c >= total) break;
+    }
+    while (c < total) {
+        // claim the following chunk now: the dispenser's latency hides behind this chunk
+        int c_next = 0;
+        if (lane == 0) c_next = atomicAdd(&ts.next_chunk[OP], 1);
         const int j = find_list(ts, c, lane);
         const unsigned long long row = ts.row[j];
         const int off4 = (c - ts.scan[j]) * kChunkV4;
@@ -388,8 +427,10 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
             const bool single = ((row_deg(row) + 3) >> 2) <= kChunkV4;   // whole list in this chunk
             if (single || __any_sync(kFull, cnt > 0)) {
                 cnt = __reduce_add_sync(kFull, cnt);
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(kFull, acc, d);
+                // per-lane acc < 16 * 2^31: two 32-bit warp reductions (REDUX) add it exactly
+                const unsigned lo16 = __reduce_add_sync(kFull, (unsigned)(acc & 0xffffull));
+                const unsigned hi = __reduce_add_sync(kFull, (unsigned)(acc >> 16));
+                acc = ((unsigned long long)hi << 16) + lo16;
                 if (lane == 0) {
                     if (single) {
                         ts.cn[j] = (int)cnt;
@@ -401,6 +442,7 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
                 }
             }
         }
+        c = __shfl_sync(kFull, c_next, 0);
     }
     return set_total;
 }
@@ -438,7 +480,14 @@ struct GroupRegs {
     int x;                      // grouping node; n_side = the "not in graph" bucket
     int p0, p1;                 // pair range of the group in grouped order
     unsigned long long xrow;    // row descriptor of x
+    int m;                      // this thread's neighbour of x in the first expansion tile, or -1
 };
+
+__device__ __forceinline__ void stage3(const SideArgs& a, GroupRegs& g, int tid) {
+    g.m = -1;
+    if (g.x < a.n_side && tid < min(kTile, row_deg(g.xrow)))
+        g.m = a.g_adj[row_first4(g.xrow) * 4 + tid];
+}
 
 __device__ __forceinline__ void stage1(const SideArgs& a, GroupRegs& g, int n_items) {
     g.x = g.item < n_items ? a.item_key[g.item] : a.n_side + 1;
@@ -475,6 +524,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
     cur.item = ts.item_next;
     stage1(a, cur, n_items);
     stage2(a, cur);
+    stage3(a, cur, tid);
 
     while (cur.item < n_items) {
         BLP_TICK(0);
@@ -502,6 +552,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             nxt.item = ts.item_next;
             stage1(a, nxt, n_items);
             stage2(a, nxt);
+            stage3(a, nxt, tid);
             cur = nxt;
             continue;
         }
@@ -529,9 +580,11 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             const int count = min(kTile, xdeg - tb);
             int nch = 0;
             if (tid < count) {
-                unsigned long long row = a.m_xrow[xadj[tb + tid]];
+                unsigned long long row = a.m_xrow[(tb == 0 && pass == 0) ? cur.m : xadj[tb + tid]];
                 if (row >> 63) {
-                    ts.hub[atomicAdd(&ts.nhub, 1)] = (int)((row >> 24) & 0x7fffffffull);
+                    const int h = atomicAdd(&ts.nhub, 1);
+                    ts.hub[h] = (int)((row >> 24) & 0x7fffffffull);
+                    ts.cn[h] = row_deg(row);   // ts.cn is idle during the expansion
                     row = 0ull;                // degree 0: skipped by both list walkers
                 }
                 ts.row[tid] = row;
@@ -549,20 +602,41 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 uint4* b4 = reinterpret_cast<uint4*>(bm);
                 const uint4* h4 = reinterpret_cast<const uint4*>(a.hub_bm);
                 const int n4 = a.bm_words >> 2;   // bm_words is a multiple of 4
+                const int hub4 = a.hub_words >> 2, lo4 = lo >> 7;
+                int first_reg = 0;   // hubs [first_reg, nhub) go through registers
                 if (nhub == 0) {
                     if (tb == 0)
                         for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
-                } else {
+                } else if (tb == 0 && !RANGED) {
+                    // first hub of the first tile: asynchronous 16-byte copies straight into the
+                    // (not yet initialised) bitmap -- every copy of the thread is in flight at
+                    // once and no register holds data; it turns on exactly deg(hub) bits
+                    const uint4* src = h4 + (size_t)ts.hub[0] * hub4;
+                    for (int i = tid; i < n4; i += NT) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(b4 + i);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
+                                     "l"(src + i)
+                                     : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (tid == 0) newbits += ts.cn[0];
+                    first_reg = 1;
+                    if (nhub > 1) {
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        // own words only: no barrier needed before OR-ing further hubs into them
+                    }
+                }
+                if (nhub > first_reg) {
+                    const bool fresh = tb == 0 && first_reg == 0;   // words not yet initialised
                     // two independent 128-bit loads in flight per thread and hub
-                    const int hub4 = a.hub_words >> 2, lo4 = lo >> 7;
                     for (int i0 = tid; i0 < n4; i0 += 2 * NT) {
                         const int i1 = i0 + NT;
                         const bool ok1 = i1 < n4;
-                        uint4 acc0 = tb == 0 ? make_uint4(0u, 0u, 0u, 0u) : b4[i0];
-                        uint4 acc1 = (tb == 0 || !ok1) ? make_uint4(0u, 0u, 0u, 0u) : b4[i1];
+                        uint4 acc0 = fresh ? make_uint4(0u, 0u, 0u, 0u) : b4[i0];
+                        uint4 acc1 = (fresh || !ok1) ? make_uint4(0u, 0u, 0u, 0u) : b4[i1];
                         newbits -= __popc(acc0.x) + __popc(acc0.y) + __popc(acc0.z) + __popc(acc0.w) +
                                    __popc(acc1.x) + __popc(acc1.y) + __popc(acc1.z) + __popc(acc1.w);
-                        for (int h = 0; h < nhub; ++h) {
+                        for (int h = first_reg; h < nhub; ++h) {
                             const uint4* src = h4 + (size_t)ts.hub[h] * hub4 + lo4;
                             const uint4 q0 = lo4 + i0 < hub4 ? __ldg(src + i0)
                                                              : make_uint4(0u, 0u, 0u, 0u);
@@ -583,6 +657,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                         if (ok1) b4[i1] = acc1;
                     }
                 }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             if (pass == 0 && tb == 0 && tid < kTile) {
                 // ts.idx / ts.aa are idle until phase 3: the first pair tile waits there
@@ -597,6 +672,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             newbits = __reduce_add_sync(kFull, newbits);
             if (lane == 0 && newbits != 0) atomicAdd(&ts.hop2cnt, newbits);
             __syncthreads();
+            if (pass == 0 && tb == 0) stage3(a, nxt, tid);
             BLP_TICK(3);
         }
 
