@@ -285,13 +285,13 @@ def main():
     n = int(pu.size)
     d_u = torch.from_numpy(pu).to(dev)
     d_b = torch.from_numpy(pv).to(dev)
-    out_u = out_b = None
+    outs = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step():
-        nonlocal out_u, out_b
-        out_u = G.score_side(_lib.SIDE_USER, d_u, d_b, want_pa=True, out=out_u)
-        out_b = G.score_side(_lib.SIDE_BUSINESS, d_u, d_b, out=out_b)
+        # the public device-resident call: both sides + pa; the business side rides a side stream
+        nonlocal outs
+        outs = G.score_pairs(d_u, d_b, out=outs)
 
     def barrier():
         if world > 1:
@@ -333,9 +333,7 @@ def main():
     # ---- final gather of the result records over NCCL (north_star), timed on its own
     gather = None
     if world > 1:
-        keys_u = ['cn', 'union', 'jaccard', 'adamic', 'pa']
-        keys_b = ['cn', 'union', 'jaccard', 'adamic']
-        srcs = [out_u[k] for k in keys_u] + [out_b[k] for k in keys_b]
+        srcs = [outs[k] for k in sorted(outs)]
         dsts = [[torch.empty_like(s) for _ in range(world)] if rank == 0 else None for s in srcs]
         for _ in range(2):
             for s, d in zip(srcs, dsts):

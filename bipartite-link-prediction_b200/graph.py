@@ -225,17 +225,38 @@ class BipartiteGraph(object):
         _lib.check(rc, 'blp_score_pairs')
         return res
 
-    def score_pairs(self, pair_u, pair_b, want_hop2=False, out=None, stream=None):
+    def score_pairs(self, pair_u, pair_b, want_hop2=False, out=None, stream=None,
+                    concurrent=True):
         """All seven reference outputs of every pair: u_cn,u_jaccard,u_adamic,b_cn,b_jaccard,
-        b_adamic,pa (plus the two union sizes).  Device tensors in, device tensors out."""
+        b_adamic,pa (plus the two union sizes).  Device tensors in, device tensors out.
+
+        With ``concurrent`` the business side is issued on a side stream (forked from and joined
+        back to ``stream``), so its grouping kernels and the tails of both scoring grids overlap.
+        """
         o_u = None if out is None else {k[2:]: v for k, v in out.items() if k.startswith('u_')}
         o_b = None if out is None else {k[2:]: v for k, v in out.items() if k.startswith('b_')}
         if out is not None and 'pa' in out:
             o_u['pa'] = out['pa']
-        ru = self.score_side(_lib.SIDE_USER, pair_u, pair_b, want_pa=True, want_hop2=want_hop2,
-                             out=o_u, stream=stream)
-        rb = self.score_side(_lib.SIDE_BUSINESS, pair_u, pair_b, want_hop2=want_hop2, out=o_b,
-                             stream=stream)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        if concurrent:
+            if getattr(self, '_side_stream', None) is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            side = self._side_stream
+            side.wait_stream(stream)
+            ru = self.score_side(_lib.SIDE_USER, pair_u, pair_b, want_pa=True,
+                                 want_hop2=want_hop2, out=o_u, stream=stream)
+            with torch.cuda.stream(side):
+                rb = self.score_side(_lib.SIDE_BUSINESS, pair_u, pair_b, want_hop2=want_hop2,
+                                     out=o_b, stream=side)
+            for t in rb.values():
+                t.record_stream(stream)
+            stream.wait_stream(side)
+        else:
+            ru = self.score_side(_lib.SIDE_USER, pair_u, pair_b, want_pa=True,
+                                 want_hop2=want_hop2, out=o_u, stream=stream)
+            rb = self.score_side(_lib.SIDE_BUSINESS, pair_u, pair_b, want_hop2=want_hop2,
+                                 out=o_b, stream=stream)
         res = {'u_' + k: v for k, v in ru.items() if k != 'pa'}
         res.update({'b_' + k: v for k, v in rb.items()})
         res['pa'] = ru['pa']
