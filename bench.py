@@ -384,6 +384,14 @@ def main():
         peak = float(peaks.get('hbm_gbs', 6650.0))
         ab = roofline.algorithmic_bytes(cfg['n_users'], cfg['n_biz'], eu, eb, pu, pv,
                                         host['u_cn'], host['b_cn'])
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+            if a.config == 'C2' and per_gpu == cfg['n_pairs']:   # the capture is of this workload
+                traffic = tj['user_side']['traffic_bytes']
+                traffic_src = tj['source']
+        except (OSError, ValueError, KeyError):
+            pass
         ku_ms = statistics.mean(score_ms_u)
         kb_ms = statistics.mean(score_ms_b)
         bytes_u = ab['user'] + ab['pa']
@@ -393,12 +401,16 @@ def main():
                 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks
                 else 'fallback 6650 GB/s (of fallback)',
-                'traffic': None, 'algorithmic_bytes_per_launch': bytes_u,
+                'traffic': traffic, 'traffic_source': traffic_src,
+                'algorithmic_bytes_per_launch': bytes_u,
                 'kernel_ms': ku_ms,
                 'business_kernel': {'kernel_ms': kb_ms, 'algorithmic_bytes_per_launch':
                                     ab['business'],
                                     'achieved': ab['business'] / (kb_ms * 1e-3) / 1e9},
                 'grouping_ms_per_step': statistics.mean(group_ms),
+                'note': 'graph (26 MB + hub bitmaps) is L2-resident: DRAM traffic is far below the '
+                        'algorithmic bytes; the kernel is latency/L1-bound, see profiles/r01_notes.md. '
+                        'The two sides run on two streams, so per-kernel event times include overlap.',
                 'whole_step': {'algorithmic_bytes': ab['total'],
                                'achieved': ab['total'] / (ms_per_step * 1e-3) / 1e9},
                 'bytes_breakdown': {k: ab[k] for k in ('expansion_user', 'stream_user',
