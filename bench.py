@@ -352,6 +352,35 @@ def main():
                   'value_with_gather': n * world / ((ms_per_step + gms) * 1e-3), 'unit': UNIT,
                   'backend': 'nccl gather, not overlapped'}
         del dsts
+        # the same with the gather overlapped: score in 4 slices, gather slice k on a side stream
+        # while slice k+1 is being scored (dist.score_and_gather_overlapped)
+        dmod = pkg('dist')
+        o2 = r2 = None
+        for _ in range(2):
+            o2, r2 = dmod.score_and_gather_overlapped(G, d_u, d_b, chunks=4, out=o2, recv=r2)
+        barrier()
+        tot = 0.0
+        reps = max(3, min(a.steps, 10))
+        for _ in range(reps):
+            flush.zero_()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            o2, r2 = dmod.score_and_gather_overlapped(G, d_u, d_b, chunks=4, out=o2, recv=r2)
+            g1.record()
+            g1.synchronize()
+            tot += g0.elapsed_time(g1)
+        barrier()
+        gt = torch.tensor([tot / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        oms = float(gt.item())
+        gather['overlapped'] = {'ms_per_step': oms, 'value': n * world / (oms * 1e-3), 'unit': UNIT,
+                                'chunks': 4, 'steps': reps,
+                                'what': 'scoring of all ranks + final NCCL gather into rank 0, '
+                                        'gather of slice k overlapped with scoring of slice k+1'}
+        if rank == 0:
+            same = all(torch.equal(r2[k][0], outs[k]) for k in outs)
+            gather['overlapped']['rank0_rows_match_unsharded_call'] = bool(same)
+        del o2, r2
 
     # ---- end to end through the host-buffer API
     sess = G.host_session(n)

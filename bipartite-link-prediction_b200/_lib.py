@@ -21,7 +21,7 @@ SIDE_USER, SIDE_BUSINESS = 0, 1
 # every symbol include/blp.h declares
 EXPORTS = ('blp_version', 'blp_last_error', 'blp_device_count', 'blp_graph_create',
            'blp_graph_destroy', 'blp_graph_info', 'blp_graph_degrees', 'blp_score_pairs',
-           'blp_score_stats')
+           'blp_score_stats', 'blp_graph_reserve_sms')
 
 
 class GraphInfo(ctypes.Structure):
@@ -107,6 +107,7 @@ def load():
     lib.blp_score_pairs.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 7
     lib.blp_score_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ScoreStats)]
+    lib.blp_graph_reserve_sms.argtypes = [ctypes.c_void_p, ctypes.c_int]
     for name in EXPORTS:
         if name not in ('blp_last_error',):
             getattr(lib, name).restype = ctypes.c_int

@@ -369,6 +369,15 @@ extern "C" int blp_graph_degrees(const blp_graph* g, int side, int32_t* host_out
     return BLP_OK;
 }
 
+extern "C" int blp_graph_reserve_sms(blp_graph* g, int n_sms) {
+    if (!g || n_sms < 0 || n_sms >= g->sm_count) {
+        blp::set_error("blp_graph_reserve_sms: bad argument");
+        return BLP_ERR_INVALID;
+    }
+    g->reserve_sms = n_sms;
+    return BLP_OK;
+}
+
 extern "C" int blp_score_stats(const blp_graph* g, int side, blp_score_stats_t* stats) {
     if (!g || !stats || (side != BLP_SIDE_USER && side != BLP_SIDE_BUSINESS)) {
         blp::set_error("blp_score_stats: bad argument");

@@ -945,6 +945,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     else if (smem * 4 + 4096 <= budget) nt = 256;
     else if (smem * 2 + 2048 <= budget) nt = 512;
     else nt = 1024;
+    const int use_sms = std::max(1, g->sm_count - g->reserve_sms);
 #define BLP_DISPATCH(NTV, RV)                                               \
     do {                                                                    \
         rc = occupancy<NTV, RV>(smem, &per_sm);                             \
@@ -952,7 +953,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
             set_error("blp_score_pairs: scoring kernel does not fit on an SM"); \
             rc = BLP_ERR_UNSUPPORTED;                                       \
         }                                                                   \
-        if (rc == BLP_OK) rc = launch_side<NTV, RV>(a, per_sm * g->sm_count, smem, st); \
+        if (rc == BLP_OK) rc = launch_side<NTV, RV>(a, per_sm * use_sms, smem, st); \
     } while (0)
     if (nt == 256) {
         if (ranged) BLP_DISPATCH(256, true); else BLP_DISPATCH(256, false);
@@ -964,7 +965,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
 #undef BLP_DISPATCH
     if (rc == BLP_OK) {
         if (cudaEventRecord(g->ev[side][2], st) == cudaSuccess) g->ev_recorded[side] = true;
-        stats.ctas = per_sm * g->sm_count;
+        stats.ctas = per_sm * use_sms;
         stats.threads_per_cta = nt;
         stats.smem_bytes = (int)smem;
         stats.kernel_launches = 4;

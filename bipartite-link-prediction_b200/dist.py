@@ -109,3 +109,72 @@ def score_sharded(graph, pair_u, pair_b, cost=None, dst=0, group=None):
     local = graph.score_pairs(du, db)
     counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
     return gather_results(local, counts, dst=dst, group=group)
+
+
+def score_and_gather_overlapped(graph, d_u, d_b, chunks=4, dst=0, group=None, out=None, recv=None,
+                                reserve_sms=8):
+    """Score this rank's pairs in `chunks` slices and gather every slice on `dst` while the next
+    one is being scored (the gather rides a side stream; NCCL moves it over NVLink).
+
+    d_u / d_b: int32 CUDA tensors, the SAME length on every rank (pad with -1 if needed).
+    Returns (out, recv): this rank's result columns and, on `dst`, dict name -> [world, n] tensor.
+    `out` / `recv` from a previous call may be passed back in to reuse the buffers.
+    `reserve_sms` SMs are kept out of the persistent scoring grids for the duration of the call,
+    so that NCCL's send/receive kernels can run beside them.
+    """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = d_u.numel()
+    dev = graph.device
+    main = torch.cuda.current_stream(dev)
+    if getattr(graph, '_comm_stream', None) is None:
+        graph._comm_stream = torch.cuda.Stream(device=dev)
+    comm = graph._comm_stream
+    dtypes = {'cn': torch.int32, 'union': torch.int32, 'jaccard': torch.float64,
+              'adamic': torch.float64}
+    keys = ['u_' + k for k in dtypes] + ['b_' + k for k in dtypes] + ['pa']
+    if out is None:
+        out = {k: torch.empty(n, dtype=dtypes.get(k[2:], torch.int64), device=dev) for k in keys}
+    if recv is None and rank == dst:
+        recv = {k: torch.empty((world, n), dtype=out[k].dtype, device=dev) for k in keys}
+    from . import _lib
+    chunks = max(1, min(int(chunks), n // 65536 or 1))
+    bounds = [(n * c) // chunks for c in range(chunks + 1)]
+    comm.wait_stream(main)
+    graph.reserve_sms(reserve_sms)
+
+    def gather_async(names, lo, hi, after):
+        ev = torch.cuda.Event()
+        ev.record(after)
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev)
+            for k in names:
+                glist = [recv[k][r, lo:hi] for r in range(world)] if rank == dst else None
+                dist.gather(out[k][lo:hi], glist, dst=dst, group=group)
+
+    # business side once over all pairs (its hop-2 sets are shared by pairs of every slice), on a
+    # side stream so that it fills in beside the user-side slices ...
+    bkeys = [k for k in keys if k.startswith('b_')]
+    ukeys = [k for k in keys if not k.startswith('b_')]
+    if getattr(graph, '_side_stream', None) is None:
+        graph._side_stream = torch.cuda.Stream(device=dev)
+    side = graph._side_stream
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        graph.score_side(_lib.SIDE_BUSINESS, d_u, d_b, out={k[2:]: out[k] for k in bkeys},
+                         stream=side)
+    # ... and the user side slice by slice, each slice's gather behind the next slice's scoring
+    for c in range(chunks):
+        lo, hi = bounds[c], bounds[c + 1]
+        if hi <= lo:
+            continue
+        ou = {(k[2:] if k.startswith('u_') else k): out[k][lo:hi] for k in ukeys}
+        graph.score_side(_lib.SIDE_USER, d_u[lo:hi], d_b[lo:hi], want_pa=True, out=ou)
+        gather_async(ukeys, lo, hi, main)
+    gather_async(bkeys, 0, n, side)
+    main.wait_stream(side)
+    graph.reserve_sms(0)
+    main.wait_stream(comm)
+    return out, recv

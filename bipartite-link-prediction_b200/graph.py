@@ -262,6 +262,10 @@ class BipartiteGraph(object):
         res['pa'] = ru['pa']
         return res
 
+    def reserve_sms(self, n_sms):
+        """Keep n_sms SMs out of the scoring grids (0 = use all); see blp_graph_reserve_sms."""
+        _lib.check(self._lib.blp_graph_reserve_sms(self._h, int(n_sms)), 'blp_graph_reserve_sms')
+
     def score_stats(self, side):
         st = _lib.ScoreStats()
         _lib.check(self._lib.blp_score_stats(self._h, side, ctypes.byref(st)), 'blp_score_stats')

@@ -125,6 +125,13 @@ int blp_score_pairs(blp_graph* g, int side,
                     int32_t* cn, int32_t* uni, double* jaccard, double* adamic,
                     int64_t* pa, int32_t* hop2_size, void* stream);
 
+/*
+ * Leave `n_sms` streaming multiprocessors out of the persistent scoring grids of this handle
+ * (0 = use all, the default).  A caller that overlaps the final result gather with scoring
+ * (NCCL's send/receive kernels need somewhere to run) reserves a few.
+ */
+int blp_graph_reserve_sms(blp_graph* g, int n_sms);
+
 /* Accounting of the most recent blp_score_pairs on this handle (per side).  The two event times
  * are valid once that call's work has completed (the function waits for its end event). */
 int blp_score_stats(const blp_graph* g, int side, blp_score_stats_t* stats);
