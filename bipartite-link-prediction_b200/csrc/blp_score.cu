@@ -19,6 +19,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "blp_internal.h"
@@ -56,11 +57,17 @@ struct SideArgs {
     int* acc_cn;
     unsigned long long* acc_aa;
     // grouping
-    const long long* __restrict__ grp_off;  // [n_side + 2]; key n_side = "not in graph"
-    const int* __restrict__ item_key;       // non-empty group keys
+    // work items: item i is the node item_key[i] (n_side = "not in graph") with the pairs
+    // [item_start[i], item_end[i]) of the grouped order
+    const int* __restrict__ item_key;
+    const int* __restrict__ item_start;
+    const int* __restrict__ item_end;
     const int* __restrict__ n_items;
-    const int* __restrict__ perm;           // caller-order pair index, grouped order
+    const int* __restrict__ perm;           // caller-order pair index per grouped position, or
+                                            // null when the grouped order IS the caller order
     const int* __restrict__ gpartner;       // partner y of every pair, grouped order
+    const int* __restrict__ mode;           // MODE_RUNS: grouped order == caller order (perm and
+    const int* __restrict__ caller_y;       //            gpartner are unused; partners = caller_y)
     int* work_counter;
     // outputs, caller order (any may be null)
     int* cn;
@@ -83,7 +90,11 @@ __device__ __forceinline__ int row_deg(unsigned long long row) { return (int)(ro
 __device__ __forceinline__ long long row_first4(unsigned long long row) { return (long long)(row >> 24); }
 
 // ---------------------------------------------------------------------------------------------
-// Grouping: counting sort of pair indices by the node whose hop-2 set they need.
+// Grouping.  Every pair gets a key: the node whose hop-2 set it needs, or n_side when an id of
+// the pair is not in the graph.  Two ways to turn keys into work items:
+//   runs   -- the pairs already arrive grouped (examples.json stores them per user): every run
+//             of equal keys is an item, the grouped order is the caller order, nothing moves;
+//   sort   -- counting sort of the pair indices by key (any order in, e.g. the business side).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int group_key(int x, int y, int n_side, int n_mid,
                                          const int* __restrict__ g_deg,
@@ -93,35 +104,85 @@ __device__ __forceinline__ int group_key(int x, int y, int n_side, int n_mid,
     return ok ? x : n_side;   // similarity.py:52,59-60: any id not in the graph -> literal 0
 }
 
-__global__ void k_group_count(const int* __restrict__ gx, const int* __restrict__ gy, long long n,
-                              int n_side, int n_mid, const int* __restrict__ g_deg,
-                              const int* __restrict__ m_deg, unsigned* __restrict__ cnt) {
+__global__ void k_group_keys(const int* __restrict__ gx, const int* __restrict__ gy, long long n,
+                             int n_side, int n_mid, const int* __restrict__ g_deg,
+                             const int* __restrict__ m_deg, int* __restrict__ keys) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) keys[i] = group_key(gx[i], gy[i], n_side, n_mid, g_deg, m_deg);
+}
+
+constexpr int kRunCut = 4096;   // runs are cut at multiples of this, bounding the serial scan below
+
+__device__ __forceinline__ bool run_starts_at(const int* __restrict__ keys, long long i) {
+    return i == 0 || (i % kRunCut) == 0 || keys[i] != keys[i - 1];
+}
+
+__global__ void k_count_runs(const int* __restrict__ keys, long long n, unsigned* __restrict__ n_runs) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned c = 0;
+    for (; i < n; i += stride) c += run_starts_at(keys, i);
+    c = __reduce_add_sync(kFull, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_runs, c);
+}
+
+// Grouping mode, decided on the device so that the call never waits for the host:
+// runs are used when they average >= 4 pairs (BLP_GROUPING=runs/sort forces a mode).
+enum { MODE_SORT = 0, MODE_RUNS = 1 };
+__global__ void k_decide_mode(const unsigned* __restrict__ n_runs, long long n, int force,
+                              int* __restrict__ mode) {
+    *mode = force >= 0 ? force : (((long long)*n_runs * 4 <= n) ? MODE_RUNS : MODE_SORT);
+}
+
+__global__ void k_runs_to_items(const int* __restrict__ mode, const int* __restrict__ keys,
+                                long long n, int* __restrict__ item_key,
+                                int* __restrict__ item_start, int* __restrict__ item_end,
+                                int* __restrict__ n_items) {
+    if (*mode != MODE_RUNS) return;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        int key = group_key(gx[i], gy[i], n_side, n_mid, g_deg, m_deg);
-        atomicAdd(&cnt[key], 1u);
+        if (!run_starts_at(keys, i)) continue;
+        const int key = keys[i];
+        long long j = i + 1;
+        while (j < n && (j % kRunCut) != 0 && keys[j] == key) ++j;
+        const int it = atomicAdd(n_items, 1);
+        item_key[it] = key;
+        item_start[it] = (int)i;
+        item_end[it] = (int)j;
     }
 }
 
-// Single-CTA exclusive scan of the group sizes; also compacts the non-empty keys.  Four keys per
-// thread and iteration (4096 per trip) keep the serial trip count low: 90 trips for 366 k keys.
-__global__ void __launch_bounds__(1024) k_group_scan(const unsigned* __restrict__ cnt, int n_keys,
-                                                     long long* __restrict__ grp_off,
-                                                     unsigned* __restrict__ cursor,
+__global__ void k_group_count(const int* __restrict__ mode, const int* __restrict__ keys,
+                              long long n, unsigned* __restrict__ cnt) {
+    if (*mode != MODE_SORT) return;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) atomicAdd(&cnt[keys[i]], 1u);
+}
+
+// Single-CTA exclusive scan of the group sizes; also compacts the non-empty keys into items.
+// Four keys per thread and iteration (4096 per trip) keep the serial trip count low.
+__global__ void __launch_bounds__(1024) k_group_scan(const int* __restrict__ mode,
+                                                     const unsigned* __restrict__ cnt, int n_keys,
+                                                     unsigned* __restrict__ grp_off,
                                                      int* __restrict__ item_key,
+                                                     int* __restrict__ item_start,
+                                                     int* __restrict__ item_end,
                                                      int* __restrict__ n_items) {
+    if (*mode != MODE_SORT) return;
     __shared__ unsigned s_sum[32];
     __shared__ int s_flag[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    long long base = 0;   // carried identically by every thread
+    unsigned base = 0;   // carried identically by every thread (n < 2^31 pairs per call)
     int fbase = 0;
     for (int start = 0; start < n_keys; start += 4096) {
         const int i0 = start + tid * 4;
         unsigned c[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) c[k] = i0 + k < n_keys ? cnt[i0 + k] : 0u;
-        unsigned v = c[0] + c[1] + c[2] + c[3];          // a trip holds < 2^32 pairs in total
+        unsigned v = c[0] + c[1] + c[2] + c[3];
         int f = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
         const unsigned own_v = v;
         const int own_f = f;
@@ -158,14 +219,18 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned* __restrict_
             wb = 0;
             fb = 0;
         }
-        long long off = base + wb + (v - own_v);          // exclusive prefix of this thread
+        unsigned off = base + wb + (v - own_v);          // exclusive prefix of this thread
         int slot = fbase + fb + (f - own_f);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (i0 + k < n_keys) {
-                grp_off[i0 + k] = off;
-                cursor[i0 + k] = 0u;
-                if (c[k] > 0) item_key[slot++] = i0 + k;
+                grp_off[i0 + k] = off;                   // doubles as the scatter cursor
+                if (c[k] > 0) {
+                    item_key[slot] = i0 + k;
+                    item_start[slot] = (int)off;
+                    item_end[slot] = (int)(off + c[k]);
+                    ++slot;
+                }
                 off += c[k];
             }
         }
@@ -173,26 +238,20 @@ __global__ void __launch_bounds__(1024) k_group_scan(const unsigned* __restrict_
         fbase += trip_flags;
         __syncthreads();
     }
-    if (tid == 0) {
-        grp_off[n_keys] = base;
-        *n_items = fbase;
-    }
+    if (tid == 0) *n_items = fbase;
 }
 
-__global__ void k_group_scatter(const int* __restrict__ gx, const int* __restrict__ gy,
-                                long long n, int n_side, int n_mid,
-                                const int* __restrict__ g_deg, const int* __restrict__ m_deg,
-                                const long long* __restrict__ grp_off,
+__global__ void k_group_scatter(const int* __restrict__ mode, const int* __restrict__ keys,
+                                const int* __restrict__ gy, long long n,
                                 unsigned* __restrict__ cursor, int* __restrict__ perm,
                                 int* __restrict__ gpartner) {
+    if (*mode != MODE_SORT) return;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        int y = gy[i];
-        int key = group_key(gx[i], y, n_side, n_mid, g_deg, m_deg);
-        long long pos = grp_off[key] + atomicAdd(&cursor[key], 1u);
+        const unsigned pos = atomicAdd(&cursor[keys[i]], 1u);   // cursor starts at the group offset
         perm[pos] = (int)i;
-        gpartner[pos] = y;
+        gpartner[pos] = gy[i];
     }
 }
 
@@ -490,16 +549,16 @@ __device__ __forceinline__ void stage3(const SideArgs& a, GroupRegs& g, int tid)
 }
 
 __device__ __forceinline__ void stage1(const SideArgs& a, GroupRegs& g, int n_items) {
-    g.x = g.item < n_items ? a.item_key[g.item] : a.n_side + 1;
+    g.x = a.n_side + 1;
+    g.p0 = g.p1 = 0;
+    if (g.item < n_items) {
+        g.x = a.item_key[g.item];
+        g.p0 = a.item_start[g.item];
+        g.p1 = a.item_end[g.item];
+    }
 }
 __device__ __forceinline__ void stage2(const SideArgs& a, GroupRegs& g) {
-    g.p0 = g.p1 = 0;
-    g.xrow = 0ull;
-    if (g.x <= a.n_side) {
-        g.p0 = (int)a.grp_off[g.x];
-        g.p1 = (int)a.grp_off[g.x + 1];
-        if (g.x < a.n_side) g.xrow = a.g_row[g.x];
-    }
+    g.xrow = g.x < a.n_side ? a.g_row[g.x] : 0ull;
 }
 
 template <int NT, bool RANGED>
@@ -510,6 +569,10 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
     TileSmem& ts = *reinterpret_cast<TileSmem*>(smem_raw + (size_t)a.bm_words * 4);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_items = *a.n_items;
+    if (*a.mode == MODE_RUNS) {   // kernel parameters are per-thread copies: patch them locally
+        a.perm = nullptr;
+        a.gpartner = a.caller_y;
+    }
 
 #ifdef BLP_PHASE_TIMING
     long long t_last = clock64();
@@ -538,7 +601,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         if (x >= a.n_side) {
             // pairs with an id that is not in the graph: every score is the literal 0
             for (long long k = p0 + tid; k < p1; k += NT) {
-                int idx = a.perm[k];
+                int idx = a.perm ? a.perm[k] : (int)k;
                 if (a.cn) a.cn[idx] = 0;
                 if (a.uni) a.uni[idx] = 0;
                 if (a.jac) a.jac[idx] = 0.0;
@@ -566,7 +629,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         int park_idx = 0;
         if (tid < kTile && p0 + tid < p1) {
             park_row = a.m_row[a.gpartner[p0 + tid]];
-            park_idx = a.perm[p0 + tid];
+            park_idx = a.perm ? a.perm[p0 + tid] : (int)(p0 + tid);
         }
 
         const int n_ranges = RANGED ? a.n_ranges : 1;
@@ -693,7 +756,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 const bool first = tb == p0 && pass == 0;
                 unsigned long long row = first ? ts.aa[tid] : a.m_row[a.gpartner[tb + tid]];
                 ts.row[tid] = row;
-                if (!first) ts.idx[tid] = a.perm[tb + tid];
+                if (!first) ts.idx[tid] = a.perm ? a.perm[tb + tid] : (int)(tb + tid);
                 ts.cn[tid] = 0;
                 ts.aa[tid] = 0ull;
                 nch = long_chunks(row);
@@ -898,43 +961,97 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         return BLP_ERR_UNSUPPORTED;
     }
 
-    // ---- stream-ordered scratch
+    // ---- stream-ordered scratch + grouping
     const int n_keys = a.n_side + 1;
-    unsigned *cnt = nullptr, *cursor = nullptr;
-    long long* grp_off = nullptr;
-    int *item_key = nullptr, *perm = nullptr, *gpartner = nullptr, *scalars = nullptr;
-    BLP_CUDA_TRY(cudaMallocAsync((void**)&cnt, sizeof(unsigned) * (size_t)n_keys, st));
-    BLP_CUDA_TRY(cudaMallocAsync((void**)&cursor, sizeof(unsigned) * (size_t)n_keys, st));
-    BLP_CUDA_TRY(cudaMallocAsync((void**)&grp_off, sizeof(long long) * ((size_t)n_keys + 1), st));
-    BLP_CUDA_TRY(cudaMallocAsync((void**)&item_key, sizeof(int) * (size_t)n_keys, st));
-    BLP_CUDA_TRY(cudaMallocAsync((void**)&perm, sizeof(int) * (size_t)n, st));
-    BLP_CUDA_TRY(cudaMallocAsync((void**)&gpartner, sizeof(int) * (size_t)n, st));
-    BLP_CUDA_TRY(cudaMallocAsync((void**)&scalars, sizeof(int) * 2, st));
-    BLP_CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
-    BLP_CUDA_TRY(cudaMemsetAsync(scalars, 0, sizeof(int) * 2, st));
+    std::vector<void*> scratch;
+    auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, st);
+        if (e == cudaSuccess) scratch.push_back(*p);
+        return e;
+    };
+    auto release = [&]() {
+        for (void* p : scratch) cudaFreeAsync(p, st);
+        scratch.clear();
+    };
+#define BLP_TRY_SCRATCH(expr)                                                    \
+    do {                                                                         \
+        cudaError_t e__ = (expr);                                                \
+        if (e__ != cudaSuccess) {                                                \
+            release();                                                           \
+            return blp::cuda_fail(e__, #expr, __FILE__, __LINE__);               \
+        }                                                                        \
+    } while (0)
+    int *keys = nullptr, *scalars = nullptr;
+    int *item_key = nullptr, *item_start = nullptr, *item_end = nullptr;
+    BLP_TRY_SCRATCH(alloc((void**)&keys, sizeof(int) * (size_t)n));
+    BLP_TRY_SCRATCH(alloc((void**)&scalars, sizeof(int) * 4));   // n_items, work counter, n_runs
+    BLP_TRY_SCRATCH(cudaMemsetAsync(scalars, 0, sizeof(int) * 4, st));
     if (ranged) {
-        BLP_CUDA_TRY(cudaMallocAsync((void**)&a.acc_cn, sizeof(int) * (size_t)n, st));
-        BLP_CUDA_TRY(cudaMallocAsync((void**)&a.acc_aa, sizeof(unsigned long long) * (size_t)n, st));
+        BLP_TRY_SCRATCH(alloc((void**)&a.acc_cn, sizeof(int) * (size_t)n));
+        BLP_TRY_SCRATCH(alloc((void**)&a.acc_aa, sizeof(unsigned long long) * (size_t)n));
     }
 
-    BLP_CUDA_TRY(cudaEventRecord(g->ev[side][0], st));
+    BLP_TRY_SCRATCH(cudaEventRecord(g->ev[side][0], st));
     const int gblocks = (int)std::min<long long>((n + 255) / 256, (long long)g->sm_count * 16);
-    k_group_count<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, g_deg, m_deg, cnt);
-    BLP_CUDA_TRY(cudaGetLastError());
-    k_group_scan<<<1, 1024, 0, st>>>(cnt, n_keys, grp_off, cursor, item_key, scalars);
-    BLP_CUDA_TRY(cudaGetLastError());
-    k_group_scatter<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, g_deg, m_deg, grp_off,
-                                             cursor, perm, gpartner);
-    BLP_CUDA_TRY(cudaGetLastError());
+    int launches = 1;
+    k_group_keys<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, g_deg, m_deg, keys);
+    BLP_TRY_SCRATCH(cudaGetLastError());
 
-    BLP_CUDA_TRY(cudaEventRecord(g->ev[side][1], st));
+    // Pairs that already arrive grouped (the reference's examples.json stores them per user) need
+    // no sort: the runs of equal keys are the work items when they average >= 4 pairs.  The
+    // decision is taken on the device (k_decide_mode); the kernels of the mode not chosen exit at
+    // once, so the call never waits for the host.
+    int force = -1;
+    if (const char* gmode = getenv("BLP_GROUPING"))   // "runs" / "sort": tuning override
+        force = !strcmp(gmode, "runs") ? MODE_RUNS : (!strcmp(gmode, "sort") ? MODE_SORT : -1);
+    if (!us && force < 0) force = MODE_SORT;   // a per-user list is never grouped by business
+    int* mode = scalars + 3;
+    if (force < 0) {
+        k_count_runs<<<gblocks, 256, 0, st>>>(keys, n, (unsigned*)(scalars + 2));
+        BLP_TRY_SCRATCH(cudaGetLastError());
+        ++launches;
+    }
+    k_decide_mode<<<1, 1, 0, st>>>((const unsigned*)(scalars + 2), n, force, mode);
+    BLP_TRY_SCRATCH(cudaGetLastError());
+    ++launches;
+    const size_t n_items_max = force == MODE_SORT ? (size_t)n_keys : std::max((size_t)n_keys, (size_t)n);
+    BLP_TRY_SCRATCH(alloc((void**)&item_key, sizeof(int) * n_items_max));
+    BLP_TRY_SCRATCH(alloc((void**)&item_start, sizeof(int) * n_items_max));
+    BLP_TRY_SCRATCH(alloc((void**)&item_end, sizeof(int) * n_items_max));
+    if (force != MODE_SORT) {
+        k_runs_to_items<<<gblocks, 256, 0, st>>>(mode, keys, n, item_key, item_start, item_end,
+                                                 scalars);
+        BLP_TRY_SCRATCH(cudaGetLastError());
+        ++launches;
+    }
+    if (force != MODE_RUNS) {
+        unsigned *cnt = nullptr, *grp_off = nullptr;
+        int *perm = nullptr, *gpartner = nullptr;
+        BLP_TRY_SCRATCH(alloc((void**)&cnt, sizeof(unsigned) * (size_t)n_keys));
+        BLP_TRY_SCRATCH(alloc((void**)&grp_off, sizeof(unsigned) * (size_t)n_keys));
+        BLP_TRY_SCRATCH(alloc((void**)&perm, sizeof(int) * (size_t)n));
+        BLP_TRY_SCRATCH(alloc((void**)&gpartner, sizeof(int) * (size_t)n));
+        BLP_TRY_SCRATCH(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
+        k_group_count<<<gblocks, 256, 0, st>>>(mode, keys, n, cnt);
+        BLP_TRY_SCRATCH(cudaGetLastError());
+        k_group_scan<<<1, 1024, 0, st>>>(mode, cnt, n_keys, grp_off, item_key, item_start,
+                                         item_end, scalars);
+        BLP_TRY_SCRATCH(cudaGetLastError());
+        k_group_scatter<<<gblocks, 256, 0, st>>>(mode, keys, gy, n, grp_off, perm, gpartner);
+        BLP_TRY_SCRATCH(cudaGetLastError());
+        launches += 3;
+        a.perm = perm;
+        a.gpartner = gpartner;
+    }
+    a.mode = mode;
+    a.caller_y = gy;
+    BLP_TRY_SCRATCH(cudaEventRecord(g->ev[side][1], st));
 
-    a.grp_off = grp_off;
     a.item_key = item_key;
+    a.item_start = item_start;
+    a.item_end = item_end;
     a.n_items = scalars;
     a.work_counter = scalars + 1;
-    a.perm = perm;
-    a.gpartner = gpartner;
 
     // ---- persistent scoring grid: as many CTAs per SM as the bitmap allows
     int per_sm = 0, nt = 0, rc = BLP_OK;
@@ -968,20 +1085,11 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         stats.ctas = per_sm * use_sms;
         stats.threads_per_cta = nt;
         stats.smem_bytes = (int)smem;
-        stats.kernel_launches = 4;
+        stats.kernel_launches = launches + 1;
         stats.range_passes = n_ranges;
     }
-    if (ranged) {
-        cudaFreeAsync(a.acc_cn, st);
-        cudaFreeAsync(a.acc_aa, st);
-    }
-    cudaFreeAsync(cnt, st);
-    cudaFreeAsync(cursor, st);
-    cudaFreeAsync(grp_off, st);
-    cudaFreeAsync(item_key, st);
-    cudaFreeAsync(perm, st);
-    cudaFreeAsync(gpartner, st);
-    cudaFreeAsync(scalars, st);
+    release();
+#undef BLP_TRY_SCRATCH
     return rc;
 }
 

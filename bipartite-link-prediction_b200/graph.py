@@ -240,17 +240,27 @@ class BipartiteGraph(object):
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
         if concurrent:
-            if getattr(self, '_side_stream', None) is None:
+            # user side (the long one) on a high-priority stream, business side on a normal one:
+            # the block scheduler serves the user grid first and lets the business grid fill in
+            # as user CTAs retire, instead of the two grids stealing each other's SM slots
+            if getattr(self, '_hi_stream', None) is None:
+                self._hi_stream = torch.cuda.Stream(device=self.device, priority=-1)
                 self._side_stream = torch.cuda.Stream(device=self.device)
-            side = self._side_stream
+            hi, side = self._hi_stream, self._side_stream
+            hi.wait_stream(stream)
             side.wait_stream(stream)
-            ru = self.score_side(_lib.SIDE_USER, pair_u, pair_b, want_pa=True,
-                                 want_hop2=want_hop2, out=o_u, stream=stream)
-            with torch.cuda.stream(side):
-                rb = self.score_side(_lib.SIDE_BUSINESS, pair_u, pair_b, want_hop2=want_hop2,
-                                     out=o_b, stream=side)
-            for t in rb.values():
+            for which in 'bu':   # business side first: its short grid drains while users group
+                if which == 'u':
+                    with torch.cuda.stream(hi):
+                        ru = self.score_side(_lib.SIDE_USER, pair_u, pair_b, want_pa=True,
+                                             want_hop2=want_hop2, out=o_u, stream=hi)
+                else:
+                    with torch.cuda.stream(side):
+                        rb = self.score_side(_lib.SIDE_BUSINESS, pair_u, pair_b,
+                                             want_hop2=want_hop2, out=o_b, stream=side)
+            for t in list(ru.values()) + list(rb.values()):
                 t.record_stream(stream)
+            stream.wait_stream(hi)
             stream.wait_stream(side)
         else:
             ru = self.score_side(_lib.SIDE_USER, pair_u, pair_b, want_pa=True,
