@@ -278,8 +278,31 @@ struct TileSmem {
 
 // Exclusive scan of `v` over the first kTile threads into ts.scan[]; ts.scan[kTile] = total.
 template <int NT>
-__device__ __forceinline__ void tile_scan(TileSmem& ts, int v, int tid) {
+__device__ __forceinline__ void tile_scan(TileSmem& ts, int v, int tid, int count) {
     const int lane = tid & 31, warp = tid >> 5;
+#ifndef BLP_NO_SMALL_SCAN
+    if (count <= 32) {
+        // the common tile (a user's few businesses, a group's 32 pairs) lives in warp 0 alone:
+        // one warp scan, one barrier
+        if (warp == 0) {
+            int inc = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(kFull, inc, d);
+                if (lane >= d) inc += t;
+            }
+            const int total = __shfl_sync(kFull, inc, 31);
+            const int ex = inc - v;
+            ts.scan[lane] = ex;
+            const int c8 = __shfl_sync(kFull, ex, (lane & 3) * 8);
+            ts.coarse[lane] = lane < 4 ? c8 : INT_MAX;
+            if (lane == 0) ts.scan[kTile] = total;
+            if (lane < 4) ts.next_chunk[lane] = 0;
+        }
+        __syncthreads();
+        return;
+    }
+#endif
     int inc = v;
     if (tid < kTile) {
 #pragma unroll
@@ -653,7 +676,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 ts.row[tid] = row;
                 nch = long_chunks(row);
             }
-            tile_scan<NT>(ts, nch, tid);
+            tile_scan<NT>(ts, nch, tid, count);
             if (pass == 0 && tb == 0) {            // stage 1 of the next group's descriptor
                 nxt.item = ts.item_next;
                 stage1(a, nxt, n_items);
@@ -761,7 +784,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 ts.aa[tid] = 0ull;
                 nch = long_chunks(row);
             }
-            tile_scan<NT>(ts, nch, tid);
+            tile_scan<NT>(ts, nch, tid, count);
             BLP_TICK(6);
             sweep_tile<NT, OP_TEST, RANGED>(a, bm, ts, count, lane, warp, lo);
             __syncthreads();
