@@ -135,22 +135,60 @@ __global__ void k_decide_mode(const unsigned* __restrict__ n_runs, long long n, 
     *mode = force >= 0 ? force : (((long long)*n_runs * 4 <= n) ? MODE_RUNS : MODE_SORT);
 }
 
-__global__ void k_runs_to_items(const int* __restrict__ mode, const int* __restrict__ keys,
-                                long long n, int* __restrict__ item_key,
-                                int* __restrict__ item_start, int* __restrict__ item_end,
-                                int* __restrict__ n_items) {
+// One CTA per kRunCut-sized segment of the pair list (runs never cross a segment boundary):
+// every thread owns 16 consecutive positions, a block scan numbers the run starts, the item slots
+// of the segment are claimed with one atomic, and a run's end is the next run's start.
+__global__ void __launch_bounds__(256) k_runs_to_items(const int* __restrict__ mode,
+                                                       const int* __restrict__ keys, long long n,
+                                                       int* __restrict__ item_key,
+                                                       int* __restrict__ item_start,
+                                                       int* __restrict__ item_end,
+                                                       int* __restrict__ n_items) {
     if (*mode != MODE_RUNS) return;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        if (!run_starts_at(keys, i)) continue;
-        const int key = keys[i];
-        long long j = i + 1;
-        while (j < n && (j % kRunCut) != 0 && keys[j] == key) ++j;
-        const int it = atomicAdd(n_items, 1);
-        item_key[it] = key;
-        item_start[it] = (int)i;
-        item_end[it] = (int)j;
+    static_assert(kRunCut == 256 * 16, "one thread owns 16 positions of a segment");
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n_seg = (n + kRunCut - 1) / kRunCut;
+    for (long long seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
+        const long long seg_lo = seg * kRunCut, seg_hi = min(n, seg_lo + kRunCut);
+        const long long lo = seg_lo + tid * 16;
+        int k[17];
+        k[0] = (lo > seg_lo && lo - 1 < seg_hi) ? keys[lo - 1] : INT_MIN;   // INT_MIN: forces a start
+#pragma unroll
+        for (int j = 0; j < 16; ++j) k[j + 1] = lo + j < seg_hi ? keys[lo + j] : INT_MIN;
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) mine += (lo + j < seg_hi) && (k[j + 1] != k[j]);
+        int inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(kFull, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int before = inc - mine, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (w < warp) before += s_warp[w];
+            total += s_warp[w];
+        }
+        if (tid == 0) s_base = atomicAdd(n_items, total);
+        __syncthreads();
+        int slot = s_base + before;
+        const int last = s_base + total - 1;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (lo + j < seg_hi && k[j + 1] != k[j]) {
+                item_key[slot] = k[j + 1];
+                item_start[slot] = (int)(lo + j);
+                if (slot > s_base) item_end[slot - 1] = (int)(lo + j);
+                ++slot;
+            }
+        }
+        if (tid == 0 && total > 0) item_end[last] = (int)seg_hi;
+        __syncthreads();
     }
 }
 
@@ -1042,7 +1080,9 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     BLP_TRY_SCRATCH(alloc((void**)&item_start, sizeof(int) * n_items_max));
     BLP_TRY_SCRATCH(alloc((void**)&item_end, sizeof(int) * n_items_max));
     if (force != MODE_SORT) {
-        k_runs_to_items<<<gblocks, 256, 0, st>>>(mode, keys, n, item_key, item_start, item_end,
+        const int rblocks = (int)std::min<long long>((n + kRunCut - 1) / kRunCut,
+                                                     (long long)g->sm_count * 8);
+        k_runs_to_items<<<rblocks, 256, 0, st>>>(mode, keys, n, item_key, item_start, item_end,
                                                  scalars);
         BLP_TRY_SCRATCH(cudaGetLastError());
         ++launches;

@@ -11,7 +11,7 @@ L.LIB_PATH = out
 graph = importlib.import_module('bipartite-link-prediction_b200.graph')
 synth = importlib.import_module('bipartite-link-prediction_b200.synth')
 cfgname = sys.argv[1] if len(sys.argv) > 1 else 'C2'
-cfg, eu, eb, pu, pv = synth.make_config(cfgname)
+cfg, eu, eb, pu, pv = synth.make_config(cfgname, n_pairs=int(sys.argv[2]) if len(sys.argv) > 2 else None)
 G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, device=0)
 lib = L.load()
 du, dv = torch.from_numpy(pu).cuda(), torch.from_numpy(pv).cuda()
