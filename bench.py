@@ -281,7 +281,20 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
+    t0 = time.perf_counter()
     G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, device=local_rank)
+    build_host_s = time.perf_counter() - t0
+    # the same graph built on the device (edge arrays already in HBM)
+    deu, deb = torch.from_numpy(eu).to(dev), torch.from_numpy(eb).to(dev)
+    graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], deu, deb, device=local_rank,
+                         build='device').close()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Gd = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], deu, deb, device=local_rank,
+                              build='device')
+    build_device_s = time.perf_counter() - t0
+    Gd.close()
+    del deu, deb
     n = int(pu.size)
     d_u = torch.from_numpy(pu).to(dev)
     d_b = torch.from_numpy(pv).to(dev)
@@ -473,7 +486,11 @@ def main():
                 'config': config, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
                 'roofline': roof, 'cpu_baseline': cpu_baseline, 'gather': gather,
                 'concurrent_sides': concurrent_sides,
-                'graph': G.info()}
+                'graph': G.info(),
+                'graph_build': {'host_builder_s': build_host_s, 'device_builder_s': build_device_s,
+                                'edge_lines': int(eu.size),
+                                'what': 'blp_graph_create (host arrays, first call: includes CUDA '
+                                        'context creation) vs blp_graph_create_device (edges in HBM)'}}
         print(json.dumps(line), flush=True)
     if sampler:
         sampler.stop()

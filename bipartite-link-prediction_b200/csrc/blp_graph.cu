@@ -131,6 +131,33 @@ static void entry_weights(const std::vector<int32_t>& adj, int32_t sentinel,
     for (size_t k = 0; k < adj.size(); ++k)
         adjw[k] = adj[k] == sentinel ? 0u : lut[deg_of_entry_side[adj[k]]];
 }
+
+// Device properties, a warm stream-ordered memory pool and the timing events of a new handle.
+int init_device_state(blp_graph* g, int device) {
+    cudaDeviceProp prop;
+    BLP_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    g->device = device;
+    g->sm_count = prop.multiProcessorCount;
+    g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    // keep stream-ordered scratch cached in the pool instead of returning it to the driver at
+    // every synchronisation (the default release threshold is 0)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+    for (int sd = 0; sd < 2; ++sd)
+        for (int k = 0; k < 3; ++k) BLP_CUDA_TRY(cudaEventCreate(&g->ev[sd][k]));
+    return BLP_OK;
+}
+
+// 1/ln(d) in Q1.31 for d = 0..max_deg (0 for d <= 1), evaluated with the host libm.
+void weight_lut(int32_t max_deg, std::vector<unsigned>& lut) {
+    lut.assign((size_t)max_deg + 1, 0u);
+    for (int32_t d = 2; d <= max_deg; ++d)
+        lut[d] = (unsigned)llrint(ldexp(1.0 / log((double)d), BLP_AA_FRAC_BITS));
+}
 }  // namespace blp
 
 extern "C" int blp_version(void) { return BLP_VERSION; }
@@ -264,29 +291,7 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
         blp::entry_weights(u_adj, n_biz, b_deg, g->max_bdeg, u_adjw);   // user rows name businesses
         blp::entry_weights(b_adj, n_users, u_deg, g->max_udeg, b_adjw); // business rows name users
 
-        cudaDeviceProp prop;
-        rc = BLP_OK;
-        cudaError_t e = cudaGetDeviceProperties(&prop, device);
-        if (e != cudaSuccess) rc = blp::cuda_fail(e, "cudaGetDeviceProperties", __FILE__, __LINE__);
-        if (rc == BLP_OK) {
-            g->sm_count = prop.multiProcessorCount;
-            g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-        }
-        if (rc == BLP_OK) {
-            // keep stream-ordered scratch cached in the pool instead of returning it to the
-            // driver at every synchronisation (the default release threshold is 0)
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-                uint64_t keep = UINT64_MAX;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            (void)cudaGetLastError();
-        }
-        for (int sd = 0; sd < 2 && rc == BLP_OK; ++sd)
-            for (int k = 0; k < 3 && rc == BLP_OK; ++k) {
-                e = cudaEventCreate(&g->ev[sd][k]);
-                if (e != cudaSuccess) rc = blp::cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__);
-            }
+        rc = blp::init_device_state(g, device);
         if (rc == BLP_OK) rc = blp::upload(&g->u_row, u_row, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->b_row, b_row, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->u_adj, u_adj, &g->device_bytes);

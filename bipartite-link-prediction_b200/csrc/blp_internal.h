@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "blp.h"
 
@@ -51,6 +52,8 @@ namespace blp {
 // words of the shared-memory bitmap over n_side nodes (+1 sentinel bit), multiple of 4
 inline int bitmap_words(int n_side) { return (int)((((long long)n_side + 1 + 31) / 32 + 3) & ~3LL); }
 int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host);
+int init_device_state(blp_graph* g, int device);
+void weight_lut(int32_t max_deg, std::vector<unsigned>& lut);
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 }  // namespace blp

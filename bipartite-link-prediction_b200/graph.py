@@ -58,23 +58,47 @@ class BipartiteGraph(object):
         (dataset_maker.py:173-174 guarantees it; hop-2 means something else otherwise).
     """
 
-    def __init__(self, n_users, n_biz, edge_u, edge_b, device=None, user_ids=None, biz_ids=None):
+    def __init__(self, n_users, n_biz, edge_u, edge_b, device=None, user_ids=None, biz_ids=None,
+                 build='host'):
+        """build='host': blp_graph_create (edge arrays on the host, C++ builder);
+        build='device': blp_graph_create_device (edge arrays in HBM -- CUDA int32 tensors are
+        taken as they are, anything else is uploaded first -- radix sort and CSR build on the GPU)."""
         lib = _lib.load()
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         if isinstance(device, torch.device):
             device = device.index or 0
-        eu = np.ascontiguousarray(np.asarray(edge_u), dtype=np.int32)
-        eb = np.ascontiguousarray(np.asarray(edge_b), dtype=np.int32)
-        if eu.shape != eb.shape or eu.ndim != 1:
-            raise ValueError('edge_u and edge_b must be 1-D arrays of equal length')
         self._lib = lib
         self._h = ctypes.c_void_p()
-        rc = lib.blp_graph_create(int(n_users), int(n_biz), int(eu.size),
-                                  eu.ctypes.data_as(ctypes.c_void_p),
-                                  eb.ctypes.data_as(ctypes.c_void_p), int(device),
-                                  ctypes.byref(self._h))
-        _lib.check(rc, 'blp_graph_create')
+        if build == 'device':
+            dev = torch.device('cuda', int(device))
+            with torch.cuda.device(dev):
+                def to_dev(x):
+                    if isinstance(x, torch.Tensor):
+                        return x.to(device=dev, dtype=torch.int32).contiguous()
+                    return torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.int32)).to(dev)
+                teu, teb = to_dev(edge_u), to_dev(edge_b)
+                if teu.shape != teb.shape or teu.dim() != 1:
+                    raise ValueError('edge_u and edge_b must be 1-D arrays of equal length')
+                st = torch.cuda.current_stream(dev)
+                rc = lib.blp_graph_create_device(int(n_users), int(n_biz), int(teu.numel()),
+                                                 ctypes.c_void_p(teu.data_ptr()),
+                                                 ctypes.c_void_p(teb.data_ptr()), int(device),
+                                                 ctypes.c_void_p(st.cuda_stream),
+                                                 ctypes.byref(self._h))
+            _lib.check(rc, 'blp_graph_create_device')
+        elif build == 'host':
+            eu = np.ascontiguousarray(np.asarray(edge_u), dtype=np.int32)
+            eb = np.ascontiguousarray(np.asarray(edge_b), dtype=np.int32)
+            if eu.shape != eb.shape or eu.ndim != 1:
+                raise ValueError('edge_u and edge_b must be 1-D arrays of equal length')
+            rc = lib.blp_graph_create(int(n_users), int(n_biz), int(eu.size),
+                                      eu.ctypes.data_as(ctypes.c_void_p),
+                                      eb.ctypes.data_as(ctypes.c_void_p), int(device),
+                                      ctypes.byref(self._h))
+            _lib.check(rc, 'blp_graph_create')
+        else:
+            raise ValueError("build must be 'host' or 'device'")
         self.device = torch.device('cuda', int(device))
         self.n_users, self.n_biz = int(n_users), int(n_biz)
         # shared-id-space view (sorted id tables), None when built from local indices
@@ -84,7 +108,7 @@ class BipartiteGraph(object):
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def from_id_edges(cls, ids_u, ids_b, device=None):
+    def from_id_edges(cls, ids_u, ids_b, device=None, build='host'):
         ids_u = np.asarray(ids_u, dtype=np.int64)
         ids_b = np.asarray(ids_b, dtype=np.int64)
         users, eu = np.unique(ids_u, return_inverse=True)
@@ -94,7 +118,8 @@ class BipartiteGraph(object):
         if np.intersect1d(users, bizs, assume_unique=True).size:
             raise ValueError('graph is not bipartite by column: some id appears both as a user '
                              '(column 0) and as a business (column 1)')
-        return cls(users.size, bizs.size, eu, eb, device=device, user_ids=users, biz_ids=bizs)
+        return cls(users.size, bizs.size, eu, eb, device=device, user_ids=users, biz_ids=bizs,
+                   build=build)
 
     @classmethod
     def from_edge_list(cls, path, src_col=0, dst_col=1, device=None):

@@ -93,6 +93,16 @@ int blp_device_count(int* count);
 int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
                      const int32_t* edge_u, const int32_t* edge_b,
                      int device, blp_graph** out);
+/*
+ * The same, with the edge arrays already in DEVICE memory and the whole construction on the GPU:
+ * 64-bit radix sort of the (user, business) keys, duplicate removal, both padded CSR directions,
+ * bank striping of the rows, per-entry weights (the step in front of the
+ * path).  Row order inside the CSR differs from the host builder's; every score is identical.
+ * `stream` is a cudaStream_t; the call returns when the handle is ready.
+ */
+int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n_edges,
+                            const int32_t* edge_u_dev, const int32_t* edge_b_dev,
+                            int device, void* stream, blp_graph** out);
 int blp_graph_destroy(blp_graph* g);
 int blp_graph_info(const blp_graph* g, blp_graph_info_t* info);
 
