@@ -601,7 +601,12 @@ struct GroupRegs {
     int p0, p1;                 // pair range of the group in grouped order
     unsigned long long xrow;    // row descriptor of x
     int m;                      // this thread's neighbour of x in the first expansion tile, or -1
+    unsigned long long rowx;    // expansion-side descriptor of m (0 when there is none)
 };
+
+__device__ __forceinline__ void stage4(const SideArgs& a, GroupRegs& g) {
+    g.rowx = g.m >= 0 ? a.m_xrow[g.m] : 0ull;
+}
 
 __device__ __forceinline__ void stage3(const SideArgs& a, GroupRegs& g, int tid) {
     g.m = -1;
@@ -643,12 +648,18 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         ts.nhub = 0;
         ts.hop2cnt = 0;
     }
+    {
+        uint4* b4 = reinterpret_cast<uint4*>(bm);
+        const int n4 = a.bm_words >> 2;
+        for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
     GroupRegs cur;
     cur.item = ts.item_next;
     stage1(a, cur, n_items);
     stage2(a, cur);
     stage3(a, cur, tid);
+    stage4(a, cur);
 
     while (cur.item < n_items) {
         BLP_TICK(0);
@@ -677,6 +688,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             stage1(a, nxt, n_items);
             stage2(a, nxt);
             stage3(a, nxt, tid);
+            stage4(a, nxt);
             cur = nxt;
             continue;
         }
@@ -704,7 +716,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             const int count = min(kTile, xdeg - tb);
             int nch = 0;
             if (tid < count) {
-                unsigned long long row = a.m_xrow[(tb == 0 && pass == 0) ? cur.m : xadj[tb + tid]];
+                unsigned long long row = (tb == 0 && pass == 0) ? cur.rowx : a.m_xrow[xadj[tb + tid]];
                 if (row >> 63) {
                     const int h = atomicAdd(&ts.nhub, 1);
                     ts.hub[h] = (int)((row >> 24) & 0x7fffffffull);
@@ -728,9 +740,9 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 const int n4 = a.bm_words >> 2;   // bm_words is a multiple of 4
                 const int hub4 = a.hub_words >> 2, lo4 = lo >> 7;
                 int first_reg = 0;   // hubs [first_reg, nhub) go through registers
+                // (the bitmap arrives all-zero: cleared at kernel start and after every group)
                 if (nhub == 0) {
-                    if (tb == 0)
-                        for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+                    // nothing to OR, and no barrier needed before the list walk
                 } else if (tb == 0 && !RANGED) {
                     // first hub of the first tile: asynchronous 16-byte copies straight into the
                     // (not yet initialised) bitmap -- every copy of the thread is in flight at
@@ -751,7 +763,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                     }
                 }
                 if (nhub > first_reg) {
-                    const bool fresh = tb == 0 && first_reg == 0;   // words not yet initialised
+                    const bool fresh = false;   // words are valid (zero or earlier hubs / tiles)
                     // two independent 128-bit loads in flight per thread and hub
                     for (int i0 = tid; i0 < n4; i0 += 2 * NT) {
                         const int i1 = i0 + NT;
@@ -788,8 +800,10 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 ts.idx[tid] = park_idx;
                 ts.aa[tid] = park_row;
             }
-            __syncthreads();
-            if (tid == 0) ts.nhub = 0;
+            if (ts.nhub > 0) {                // uniform: written before tile_scan's barrier
+                __syncthreads();              // plain hub stores before the atomics of the walk
+                if (tid == 0) ts.nhub = 0;
+            }
             if (pass == 0 && tb == 0) stage2(a, nxt);
             BLP_TICK(2);
             newbits += (int)sweep_tile<NT, OP_SET, RANGED>(a, bm, ts, count, lane, warp, lo);
@@ -823,6 +837,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 nch = long_chunks(row);
             }
             tile_scan<NT>(ts, nch, tid, count);
+            if (pass == 0 && tb == p0) stage4(a, nxt);
             BLP_TICK(6);
             sweep_tile<NT, OP_TEST, RANGED>(a, bm, ts, count, lane, warp, lo);
             __syncthreads();
@@ -855,6 +870,12 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             }
             __syncthreads();
             BLP_TICK(8);
+        }
+        // leave the bitmap all-zero for the next group / pass (ordered by its tile_scan barrier)
+        {
+            uint4* b4 = reinterpret_cast<uint4*>(bm);
+            const int n4 = a.bm_words >> 2;
+            for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         }   // id-range passes
         if (tid == 0) ts.hop2cnt = 0;   // ordered before the next group's counting by its barriers
