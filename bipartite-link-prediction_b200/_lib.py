@@ -12,7 +12,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, 'csrc')
 INCLUDE = os.path.join(_ROOT, 'include')
 LIB_PATH = os.path.join(_HERE, 'libblp.so')
-SOURCES = ('blp_graph.cu', 'blp_build.cu', 'blp_score.cu')
+SOURCES = ('blp_graph.cu', 'blp_build.cu', 'blp_score.cu', 'blp_hop3.cu')
 
 BLP_OK = 0
 BLP_ERR_INVALID, BLP_ERR_CUDA, BLP_ERR_OOM, BLP_ERR_RANGE, BLP_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
@@ -21,7 +21,8 @@ SIDE_USER, SIDE_BUSINESS = 0, 1
 # every symbol include/blp.h declares
 EXPORTS = ('blp_version', 'blp_last_error', 'blp_device_count', 'blp_graph_create',
            'blp_graph_destroy', 'blp_graph_info', 'blp_graph_degrees', 'blp_score_pairs',
-           'blp_score_stats', 'blp_graph_reserve_sms', 'blp_graph_create_device')
+           'blp_score_stats', 'blp_graph_reserve_sms', 'blp_graph_create_device',
+           'blp_hop3_count', 'blp_hop3_fill')
 
 
 class GraphInfo(ctypes.Structure):
@@ -104,6 +105,10 @@ def load():
     lib.blp_graph_create_device.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.blp_hop3_count.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                   ctypes.c_void_p, ctypes.c_void_p]
+    lib.blp_hop3_fill.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p]
     lib.blp_graph_destroy.argtypes = [ctypes.c_void_p]
     lib.blp_graph_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(GraphInfo)]
     lib.blp_graph_degrees.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]

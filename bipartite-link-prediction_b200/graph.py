@@ -297,6 +297,33 @@ class BipartiteGraph(object):
         res['pa'] = ru['pa']
         return res
 
+    def hop3_candidates(self, users, stream=None):
+        """Businesses at BFS distance exactly 3 of every user (local indices; int32 CUDA tensor or
+        array) -- make_examples' snap.GetNodesAtHop(G, u, 3, ...) (dataset_maker.py:137-139).
+        Returns (offsets int64 [n+1], businesses int32 [total]) as CUDA tensors; the candidates
+        of users[i] are businesses[offsets[i]:offsets[i+1]], ascending."""
+        if not isinstance(users, torch.Tensor):
+            users = torch.from_numpy(np.ascontiguousarray(users, dtype=np.int32))
+        users = users.to(device=self.device, dtype=torch.int32).contiguous()
+        n = users.numel()
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        sp = ctypes.c_void_p(stream.cuda_stream)
+        with torch.cuda.device(self.device):
+            counts = torch.zeros(n, dtype=torch.int64, device=self.device)
+            _lib.check(self._lib.blp_hop3_count(self._h, ctypes.c_void_p(users.data_ptr()), n,
+                                                ctypes.c_void_p(counts.data_ptr()), sp),
+                       'blp_hop3_count')
+            offsets = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
+            torch.cumsum(counts, 0, out=offsets[1:])
+            total = int(offsets[-1].item())
+            out = torch.empty(max(total, 1), dtype=torch.int32, device=self.device)
+            _lib.check(self._lib.blp_hop3_fill(self._h, ctypes.c_void_p(users.data_ptr()), n,
+                                               ctypes.c_void_p(offsets.data_ptr()),
+                                               ctypes.c_void_p(out.data_ptr()), sp),
+                       'blp_hop3_fill')
+        return offsets, out[:total]
+
     def reserve_sms(self, n_sms):
         """Keep n_sms SMs out of the scoring grids (0 = use all); see blp_graph_reserve_sms."""
         _lib.check(self._lib.blp_graph_reserve_sms(self._h, int(n_sms)), 'blp_graph_reserve_sms')

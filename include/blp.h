@@ -136,6 +136,19 @@ int blp_score_pairs(blp_graph* g, int side,
                     int64_t* pa, int32_t* hop2_size, void* stream);
 
 /*
+ * Candidate generation: the businesses at BFS distance exactly 3
+ * of each given user -- snap.GetNodesAtHop(G, u, 3, ...) of make_examples (dataset_maker.py:137-139),
+ * i.e. N(hop2(u)) minus N(u).  Variable-length output, two calls:
+ *   blp_hop3_count : counts[i] = |hop3(users[i])|                      (0 for ids not in the graph)
+ *   blp_hop3_fill  : out_biz[offsets[i] .. offsets[i+1]) = hop3(users[i]) in ascending order,
+ *                    offsets = exclusive prefix sum of counts (n+1 entries)
+ * users / counts / offsets / out_biz are DEVICE arrays; `stream` is a cudaStream_t.
+ */
+int blp_hop3_count(blp_graph* g, const int32_t* users, int64_t n, int64_t* counts, void* stream);
+int blp_hop3_fill(blp_graph* g, const int32_t* users, int64_t n, const int64_t* offsets,
+                  int32_t* out_biz, void* stream);
+
+/*
  * Leave `n_sms` streaming multiprocessors out of the persistent scoring grids of this handle
  * (0 = use all, the default).  A caller that overlaps the final result gather with scoring
  * (NCCL's send/receive kernels need somewhere to run) reserves a few.

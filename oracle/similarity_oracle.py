@@ -222,6 +222,13 @@ def main(example_file, graph_file, u_methods, u_outfiles, b_methods, b_outfiles,
              reproduce_reference_bug=reproduce_reference_bug)
 
 
+def hop3_candidates(G, u):
+    # dataset_maker.py:137-139 -- snap.GetNodesAtHop(G, u, 3, candidate_businesses, True):
+    # the businesses at BFS distance exactly 3 of user u (test infrastructure for the device-side
+    # candidate generator)
+    return set(G.nodes_at_hop(u, 3))
+
+
 def load_json(fname):
     with open(fname) as f:                               # util.py:12-15
         return json.loads(f.read())

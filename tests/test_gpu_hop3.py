@@ -1,0 +1,70 @@
+"""Device-side candidate generation (blp_hop3_*) against the BFS of Oracle A."""
+import time
+
+import numpy as np
+import pytest
+
+from conftest import pkg
+from test_gpu_parity import mods  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def test_hop3_sets_match_bfs(mods):
+    from oracle import similarity_oracle as oa
+    graph, synth = mods
+    for seed, n_users, n_biz, n_rev in ((0, 400, 90, 1500), (1, 3000, 60, 5000), (2, 60, 700, 900)):
+        eu, eb = synth.make_graph(n_users, n_biz, n_rev, seed=seed, shift_u=2.0, shift_b=2.0)
+        G = graph.BipartiteGraph(n_users, n_biz, eu, eb)
+        ids_eu, ids_eb = synth.shared_ids(n_users, eu, eb)
+        O = oa.MiniSnapGraph.from_edges(zip(ids_eu.tolist(), ids_eb.tolist()))
+        users = np.arange(-1, n_users + 1, dtype=np.int32)      # includes two ids not in the graph
+        off, biz = G.hop3_candidates(users)
+        off, biz = off.cpu().numpy(), biz.cpu().numpy()
+        assert off[0] == 0 and off[-1] == biz.size
+        in_graph = set(O.node_ids())
+        for i, u in enumerate(users.tolist()):
+            got = biz[off[i]:off[i + 1]]
+            want = (sorted(b - n_users for b in oa.hop3_candidates(O, u))
+                    if 0 <= u < n_users and u in in_graph else [])
+            assert got.tolist() == want, (seed, u)
+
+
+def test_make_examples_structure_and_timing(mods):
+    from oracle import similarity_oracle as oa
+    graph, synth = mods
+    dataset = pkg('dataset')
+    cfg, eu, eb, _, _ = synth.make_config('C1', n_pairs=1000)
+    n_users = cfg['n_users']
+    ids_eu, ids_eb = synth.shared_ids(n_users, eu, eb)
+    G = graph.BipartiteGraph.from_id_edges(ids_eu, ids_eb)
+    rng = np.random.default_rng(1)
+    users = rng.choice(G.user_ids, size=2000, replace=False)
+    # future edges: some true hop-3 pairs of the first users (positives) and some that are not
+    O = oa.MiniSnapGraph.from_edges(zip(ids_eu.tolist(), ids_eb.tolist()))
+    t0 = time.perf_counter()
+    cand = {int(u): oa.hop3_candidates(O, int(u)) for u in users[:200]}
+    t_cpu = (time.perf_counter() - t0) / 200
+    new_u, new_b = [], []
+    for u in users[:50]:
+        for b in sorted(cand[int(u)])[:3]:
+            new_u.append(int(u))
+            new_b.append(b)
+    new_u += [int(users[0])] * 2
+    new_b += [int(G.biz_ids[0]), int(G.biz_ids[-1])]
+    t0 = time.perf_counter()
+    ex = dataset.make_examples(G, users, new_u, new_b, negative_sample_rate=0.05, seed=3)
+    t_gpu = (time.perf_counter() - t0) / users.size
+    print('hop-3 candidates per user: oracle BFS %.2f ms, device path %.3f ms' % (t_cpu * 1e3, t_gpu * 1e3))
+    n_pos = 0
+    for u in users[:200]:
+        row = ex.get(str(int(u)), {})
+        for b, y in row.items():
+            assert int(b) in cand[int(u)]                       # only hop-3 businesses appear
+            n_pos += y
+        for b in sorted(cand[int(u)])[:3] if u in users[:50] else []:
+            assert row[str(b)] == 1                             # every future hop-3 edge is kept
+    assert n_pos >= 150
+    total = sum(len(v) for v in ex.values())
+    all_c = sum(len(v) for v in cand.values()) / 200 * users.size
+    assert 0.02 * all_c < total < 0.09 * all_c                  # ~5 % of the negatives survive
