@@ -345,7 +345,7 @@ def main():
     value = n * world / (ms_per_step * 1e-3)
 
     # ---- supplementary: the same call with the two sides on two streams (grids overlap)
-    for _ in range(2):
+    for _ in range(6):          # the two-stream pattern grows the stream-ordered pool first
         step(concurrent=True)
     barrier()
     c_ms = 0.0
