@@ -449,12 +449,13 @@ def main():
         peak = float(peaks.get('hbm_gbs', 6650.0))
         ab = roofline.algorithmic_bytes(cfg['n_users'], cfg['n_biz'], eu, eb, pu, pv,
                                         host['u_cn'], host['b_cn'])
-        traffic, traffic_src = None, None
+        traffic, traffic_src, phase = None, None, None
         try:
             tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
             if a.config == 'C2' and per_gpu == cfg['n_pairs']:   # the capture is of this workload
                 traffic = tj['user_side']['traffic_bytes']
                 traffic_src = tj['source']
+                phase = tj.get('phase_shares_user_side')
         except (OSError, ValueError, KeyError):
             pass
         ku_ms = statistics.mean(score_ms_u)
@@ -480,6 +481,18 @@ def main():
                 'bytes_breakdown': {k: ab[k] for k in ('expansion_user', 'stream_user',
                                                        'expansion_business', 'stream_business',
                                                        'pa', 'invalid')}}
+        if phase:
+            # "for the intersection kernel use the per-pair terms only over K2's own
+            # time".  Expansion and intersection are fused in one launch here, so K2's own time is
+            # DERIVED: this run's kernel time x the intersection sweep's share of CTA cycles,
+            # measured once with the instrumented build (tools/phase_time.py).
+            t_int = ku_ms * phase['intersection_sweep']
+            roof['intersection_phase'] = {
+                'derived': True, 'share_of_kernel': phase['intersection_sweep'],
+                'share_source': phase['source'], 'time_ms': t_int,
+                'algorithmic_bytes': ab['stream_user'],
+                'achieved': ab['stream_user'] / (t_int * 1e-3) / 1e9,
+                'frac': ab['stream_user'] / (t_int * 1e-3) / 1e9 / peak}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps,
                 'warmup': a.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic',
