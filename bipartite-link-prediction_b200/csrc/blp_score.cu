@@ -30,7 +30,10 @@ namespace blp {
 #define BLP_TILE 256
 #endif
 constexpr int kTile = BLP_TILE;   // adjacency lists per scheduling tile (<= threads per CTA)
-constexpr int kChunkV4 = 128;     // int4 loads per chunk (4 per lane): 512 ids
+#ifndef BLP_CHUNK_V4
+#define BLP_CHUNK_V4 128
+#endif
+constexpr int kChunkV4 = BLP_CHUNK_V4;   // int4 loads per chunk (at most 4 per lane): 512 ids
 constexpr unsigned kFull = 0xffffffffu;
 
 struct SideArgs {
@@ -549,7 +552,7 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
         unsigned long long acc = 0ull;
         // two halves of 256 ids: four 128-bit loads in flight per lane, half the registers
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < kChunkV4 / 64; ++half) {
             if (64 * half < n) {
                 int4 v[2];
                 uint4 wt[2];

@@ -39,11 +39,12 @@ def LoadEdgeList(graph_type, graph_file, src_col=0, dst_col=1, device=None):
 
 
 def main(example_file, graph_file, u_methods, u_outfiles, b_methods, b_outfiles, *,
-         device=None, reproduce_reference_bug=False):
+         device=None, reproduce_reference_bug=False, sidecar=False):
     examples = util.load_json(example_file)
     G = LoadEdgeList(PUNGraph, graph_file, 0, 1, device=device)
-    users(examples, G, u_methods, u_outfiles)
-    business(examples, G, b_methods, b_outfiles, reproduce_reference_bug=reproduce_reference_bug)
+    users(examples, G, u_methods, u_outfiles, sidecar=sidecar)
+    business(examples, G, b_methods, b_outfiles, reproduce_reference_bug=reproduce_reference_bug,
+             sidecar=sidecar)
     return G
 
 
@@ -73,7 +74,8 @@ def _score_side(G, side, ids_u, ids_b):
     return host, in_graph
 
 
-def _emit(examples, keys_u, keys_b, host, in_graph, methods, outfiles, skip_in_graph=()):
+def _emit(examples, keys_u, keys_b, host, in_graph, methods, outfiles, skip_in_graph=(),
+          sidecar=False):
     out = []
     for m, f in zip(methods, outfiles):
         sim = defaultdict(dict)
@@ -96,24 +98,29 @@ def _emit(examples, keys_u, keys_b, host, in_graph, methods, outfiles, skip_in_g
                 else:
                     sim[u][v] = int(vals[i])            # cn, pa, and adamic's untouched int 0
         util.write_json(sim, f)
+        if sidecar:   # columnar copy beside the JSON; same content, no parsing
+            u, b, v, im = util.dict_to_columns(sim)
+            np.savez(f[:-5] + '.npz' if f.endswith('.json') else f + '.npz', u=u, b=b, v=v,
+                     int_mask=im)
         out.append(sim)
     return out
 
 
-def users(examples, G, methods, outfiles):
+def users(examples, G, methods, outfiles, *, sidecar=False):
     keys_u, keys_b, ids_u, ids_b = _flatten(examples)
     host, in_graph = _score_side(G, _lib.SIDE_USER, ids_u, ids_b)
-    return _emit(examples, keys_u, keys_b, host, in_graph, methods, outfiles)
+    return _emit(examples, keys_u, keys_b, host, in_graph, methods, outfiles, sidecar=sidecar)
 
 
-def business(examples, G, methods, outfiles, *, reproduce_reference_bug=False):
+def business(examples, G, methods, outfiles, *, reproduce_reference_bug=False, sidecar=False):
     """``reproduce_reference_bug=True`` omits in-graph ``adamic_adar`` entries exactly as the
     reference's mistyped branch does (similarity.py:102); the default writes the intended score
     (similarity.py:103)."""
     keys_u, keys_b, ids_u, ids_b = _flatten(examples)
     host, in_graph = _score_side(G, _lib.SIDE_BUSINESS, ids_u, ids_b)
     skip = ('adamic_adar',) if reproduce_reference_bug else ()
-    return _emit(examples, keys_u, keys_b, host, in_graph, methods, outfiles, skip_in_graph=skip)
+    return _emit(examples, keys_u, keys_b, host, in_graph, methods, outfiles, skip_in_graph=skip,
+                 sidecar=sidecar)
 
 
 # ----------------------------------------------------------------------------- set-level API

@@ -37,7 +37,10 @@ def test_file_level_drop_in_matches_oracle_files(mods, tmp_path):
         mine = [[str(tmp_path / ('%s_%s_mine%d.json' % (s, n, bug))) for n in names] for s in 'ub']
         ref = [[str(tmp_path / ('%s_%s_ref%d.json' % (s, n, bug))) for n in names] for s in 'ub']
         sim.main(str(tmp_path / 'examples.json'), str(tmp_path / 'graph.txt'), M, mine[0], M,
-                 mine[1], reproduce_reference_bug=bug)
+                 mine[1], reproduce_reference_bug=bug, sidecar=True)
+        # the columnar sidecar converts back to the very same JSON text
+        util.npz_to_json(mine[0][2][:-5] + '.npz', str(tmp_path / 'roundtrip.json'))
+        assert open(str(tmp_path / 'roundtrip.json')).read() == open(mine[0][2]).read()
         oa.main(str(tmp_path / 'examples.json'), str(tmp_path / 'graph.txt'), M, ref[0], M, ref[1],
                 reproduce_reference_bug=bug)
         for fm, fr in zip(mine[0] + mine[1], ref[0] + ref[1]):

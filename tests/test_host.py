@@ -79,6 +79,22 @@ def test_json_formats_round_trip(tmp_path):
     assert u.tolist() == [0, 5] and b.tolist() == [10, 12]
 
 
+def test_columnar_sidecar_is_lossless(tmp_path):
+    """JSON -> npz -> JSON reproduces the reference's score file byte for byte (types included)."""
+    util = pkg('util')
+    scores = {'3': {'10': 2, '11': 0.5, '12': 0}, '7': {'10': 0, '13': 1.4426950408889634},
+              '9': {'11': 0.0}}
+    fj, fn, fb = (str(tmp_path / n) for n in ('s.json', 's.npz', 'back.json'))
+    util.write_json(scores, fj)
+    util.json_to_npz(fj, fn)
+    util.npz_to_json(fn, fb)
+    assert open(fb).read() == open(fj).read()
+    back = util.load_json(fb)
+    assert isinstance(back['3']['12'], int) and isinstance(back['9']['11'], float)
+    u, b, v, im = util.dict_to_columns(scores)
+    assert u.tolist() == [3, 3, 3, 7, 7, 9] and im.tolist() == [True, False, True, True, False, False]
+
+
 def test_set_level_functions_keep_reference_meaning():
     sim = pkg('similarity')
 
