@@ -138,7 +138,7 @@ def adamic_adar(setone, settwo, G):
     for i in setone & settwo:
         deg = G.GetNI(i).GetDeg()
         if deg > 1:
-            total += 1.0 / math.log(deg)
+            total += (math.log(deg)) ** -1      # the reference's exact expression (similarity.py:123)
     return total
 
 
