@@ -12,7 +12,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, 'csrc')
 INCLUDE = os.path.join(_ROOT, 'include')
 LIB_PATH = os.path.join(_HERE, 'libblp.so')
-SOURCES = ('blp_graph.cu', 'blp_build.cu', 'blp_score.cu', 'blp_hop3.cu')
+SOURCES = ('blp_graph.cu', 'blp_build.cu', 'blp_score.cu', 'blp_hop3.cu', 'blp_eval.cu')
 
 BLP_OK = 0
 BLP_ERR_INVALID, BLP_ERR_CUDA, BLP_ERR_OOM, BLP_ERR_RANGE, BLP_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
@@ -22,7 +22,7 @@ SIDE_USER, SIDE_BUSINESS = 0, 1
 EXPORTS = ('blp_version', 'blp_last_error', 'blp_device_count', 'blp_graph_create',
            'blp_graph_destroy', 'blp_graph_info', 'blp_graph_degrees', 'blp_score_pairs',
            'blp_score_stats', 'blp_graph_reserve_sms', 'blp_graph_create_device',
-           'blp_hop3_count', 'blp_hop3_fill')
+           'blp_hop3_count', 'blp_hop3_fill', 'blp_eval_precision_at_k', 'blp_eval_roc_auc')
 
 
 class GraphInfo(ctypes.Structure):
@@ -109,6 +109,11 @@ def load():
                                    ctypes.c_void_p, ctypes.c_void_p]
     lib.blp_hop3_fill.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                   ctypes.c_void_p, ctypes.c_void_p]
+    lib.blp_eval_precision_at_k.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
+                                            ctypes.c_void_p]
+    lib.blp_eval_roc_auc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                     ctypes.POINTER(ctypes.c_uint64), ctypes.c_void_p]
     lib.blp_graph_destroy.argtypes = [ctypes.c_void_p]
     lib.blp_graph_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(GraphInfo)]
     lib.blp_graph_degrees.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]

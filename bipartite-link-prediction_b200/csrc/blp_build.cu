@@ -370,6 +370,40 @@ int bits_for(unsigned v) {
 }
 
 }  // namespace
+
+// Sorts n 64-bit keys ascending on the bits named by `shifts` (8 bits from each shift, least
+// significant group first).  `keys` and `tmp` are device buffers of n entries; the sorted keys
+// end up where *sorted points (one of the two).  Stream-ordered, no host synchronisation.
+int radix_sort_u64(unsigned long long* keys, unsigned long long* tmp, long long n,
+                   const std::vector<int>& shifts, cudaStream_t st, unsigned long long** sorted) {
+    *sorted = keys;
+    if (n <= 1 || shifts.empty()) return BLP_OK;
+    const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
+    unsigned* hist = nullptr;
+    unsigned long long* hbase = nullptr;
+    BLP_CUDA_TRY(cudaMallocAsync((void**)&hist, sizeof(unsigned) * 256 * (size_t)n_tiles, st));
+    cudaError_t e = cudaMallocAsync((void**)&hbase, sizeof(unsigned long long) * 256 * (size_t)n_tiles, st);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(hist, st);
+        return cuda_fail(e, "cudaMallocAsync(hbase)", __FILE__, __LINE__);
+    }
+    Scanner scan;
+    scan.st = st;
+    int rc = BLP_OK;
+    for (int s : shifts) {
+        k_radix_hist<<<n_tiles, 256, 0, st>>>(keys, n, s, n_tiles, hist);
+        rc = scan.run(hist, 256LL * n_tiles, false, hbase, nullptr);
+        if (rc != BLP_OK) break;
+        k_radix_scatter<<<n_tiles, 256, 0, st>>>(keys, tmp, n, s, n_tiles, hbase);
+        std::swap(keys, tmp);
+    }
+    if (rc == BLP_OK && cudaGetLastError() != cudaSuccess) rc = BLP_ERR_CUDA;
+    scan.release();
+    cudaFreeAsync(hist, st);
+    cudaFreeAsync(hbase, st);
+    *sorted = keys;
+    return rc;
+}
 }  // namespace blp
 
 extern "C" int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n_edges,
@@ -456,22 +490,13 @@ extern "C" int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n
     }
 
     // ---- LSD radix sort over the bits in use: business bits, then user bits
-    if (n > 1) {
-        const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
-        unsigned* hist = nullptr;
-        unsigned long long* hbase = nullptr;
-        BLP_TRY_B(alloc((void**)&hist, sizeof(unsigned) * 256 * (size_t)n_tiles));
-        BLP_TRY_B(alloc((void**)&hbase, sizeof(unsigned long long) * 256 * (size_t)n_tiles));
+    {
         std::vector<int> shifts;
         for (int s = 0; s < bits_for((unsigned)n_biz); s += 8) shifts.push_back(s);
         for (int s = 0; s < bits_for((unsigned)n_users); s += 8) shifts.push_back(32 + s);
-        for (int s : shifts) {
-            k_radix_hist<<<n_tiles, 256, 0, st>>>(keys, n, s, n_tiles, hist);
-            BLP_RC_B(scan.run(hist, 256LL * n_tiles, false, hbase, nullptr));
-            k_radix_scatter<<<n_tiles, 256, 0, st>>>(keys, keys2, n, s, n_tiles, hbase);
-            BLP_TRY_B(cudaGetLastError());
-            std::swap(keys, keys2);
-        }
+        unsigned long long* sorted = keys;
+        BLP_RC_B(radix_sort_u64(keys, keys2, n, shifts, st, &sorted));
+        if (sorted != keys) std::swap(keys, keys2);
     }
 
     // ---- distinct edges, degrees

@@ -54,6 +54,8 @@ inline int bitmap_words(int n_side) { return (int)((((long long)n_side + 1 + 31)
 int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host);
 int init_device_state(blp_graph* g, int device);
 void weight_lut(int32_t max_deg, std::vector<unsigned>& lut);
+int radix_sort_u64(unsigned long long* keys, unsigned long long* tmp, long long n,
+                   const std::vector<int>& shifts, cudaStream_t st, unsigned long long** sorted);
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 }  // namespace blp

@@ -149,6 +149,21 @@ int blp_hop3_fill(blp_graph* g, const int32_t* users, int64_t n, const int64_t* 
                   int32_t* out_biz, void* stream);
 
 /*
+ * Evaluation: what eval.run_evaluation (eval.py:10-32) computes from
+ * one score file, on DEVICE arrays in the file's iteration order.
+ *   blp_eval_precision_at_k : offsets (n_groups+1) delimit each user's pairs; precision_out[g] =
+ *       mean label of the first min(k, #pairs) entries of a stable descending sort by score
+ *       (eval.py:21-24).  The caller sums precision_out and divides by the number of users.
+ *   blp_eval_roc_auc : counts4_host (HOST, 4 x uint64) = { #positives, #negatives,
+ *       #(pos, neg) pairs with s+ > s-, #(pos, neg) pairs with s+ == s- };
+ *       roc_auc_score (eval.py:26) = (counts[2] + counts[3]/2) / (counts[0] * counts[1]).
+ */
+int blp_eval_precision_at_k(const int64_t* offsets, const int32_t* labels, const double* scores,
+                            int64_t n_groups, int32_t k, double* precision_out, void* stream);
+int blp_eval_roc_auc(const int32_t* labels, const double* scores, int64_t n,
+                     uint64_t* counts4_host, void* stream);
+
+/*
  * Leave `n_sms` streaming multiprocessors out of the persistent scoring grids of this handle
  * (0 = use all, the default).  A caller that overlaps the final result gather with scoring
  * (NCCL's send/receive kernels need somewhere to run) reserves a few.
