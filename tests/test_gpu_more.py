@@ -211,3 +211,24 @@ def test_full_c2_properties(mods):
     r2 = G.score_pairs(du, dv)
     for k in r2:
         assert torch.equal(r[k], r2[k]), k
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize('name,n_pairs,n_check', [('C3', 2_000_000, 40_000), ('C4', 1_000_000, 15_000)])
+def test_large_configs_sampled_parity(mods, name, n_pairs, n_check):
+    """BASELINE.json configs[2] (Yelp-2019 shape: 200 KB hop-2 bitmap, one 1024-thread CTA per SM)
+    and configs[3] (heavy tail: hub businesses above 100k users) -- the full graph, a slice of the
+    pair list on the GPU, a strided sample of it against the C oracle."""
+    from oracle import c_oracle
+    graph, synth = mods
+    lib = pkg('_lib')
+    cfg, eu, eb, pu, pv = synth.make_config(name, n_pairs=n_pairs)
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    info = G.info()
+    if name == 'C4':
+        assert info['max_biz_degree'] > 100_000            # the hubs the config is about
+    got = G.score_pairs_host(pu, pv)
+    assert G.score_stats(lib.SIDE_USER)['threads_per_cta'] == 1024
+    idx = np.arange(0, pu.size, pu.size // n_check)[:n_check]
+    want = c_oracle.score_pair_arrays(cfg['n_users'], cfg['n_biz'], eu, eb, pu[idx], pv[idx])
+    check_against({k: v[idx] for k, v in got.items()}, want, idx.size)
