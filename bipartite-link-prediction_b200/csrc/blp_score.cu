@@ -959,7 +959,9 @@ __global__ void k_build_hub_bitmaps(const int* __restrict__ hub_nodes, int n_hub
 // Picks the hubs of both sides and builds their bitmaps on the device.
 // Cost model (measured on C2, profiles/r01_notes.md): walking a list costs ~0.35 L1 wavefronts per
 // id (two sweeps, bank-conflicted bitmap probes), OR-ing a bitmap costs bm_bytes/128 wavefronts,
-// so a list pays off as a bitmap from deg >= bm_bytes/45 on.
+// so by that model a list pays off as a bitmap from deg >= bm_bytes/45 on; measured on C2 with the
+// final list walker (batched probes, counted atomics) the optimum sits at bm_bytes/30
+// (user side: deg >= 1016 6.71 ms, >= 1500 6.50 ms, >= 2500 6.56 ms; business side flat).
 int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host) {
     for (int side = 0; side < 2; ++side) {
         const bool us = side == BLP_SIDE_USER;
@@ -968,7 +970,7 @@ int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host
         const int* mdeg = us ? b_deg_host : u_deg_host;
         const int words = bitmap_words(n_side);
         const long long bm_bytes = (long long)words * 4;
-        int min_deg = (int)std::max<long long>(64, bm_bytes / 45);
+        int min_deg = (int)std::max<long long>(64, bm_bytes / 30);
         if (const char* e = getenv("BLP_HUB_MIN_DEG")) min_deg = atoi(e);   // tuning override
         std::vector<int> hubs;
         if (min_deg > 0)
