@@ -282,7 +282,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     t0 = time.perf_counter()
-    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, device=local_rank)
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, device=local_rank, build='host')
     build_host_s = time.perf_counter() - t0
     # the same graph built on the device (edge arrays already in HBM)
     deu, deb = torch.from_numpy(eu).to(dev), torch.from_numpy(eb).to(dev)

@@ -59,10 +59,11 @@ class BipartiteGraph(object):
     """
 
     def __init__(self, n_users, n_biz, edge_u, edge_b, device=None, user_ids=None, biz_ids=None,
-                 build='host'):
-        """build='host': blp_graph_create (edge arrays on the host, C++ builder);
-        build='device': blp_graph_create_device (edge arrays in HBM -- CUDA int32 tensors are
-        taken as they are, anything else is uploaded first -- radix sort and CSR build on the GPU)."""
+                 build='device'):
+        """build='device' (default): blp_graph_create_device -- CUDA int32 tensors are taken as they
+        are, anything else is uploaded first; radix sort and CSR build run on the GPU (6-11x faster
+        than the host builder on C2/C3);  build='host': blp_graph_create (C++ builder on the host
+        arrays).  Both yield the same scores."""
         lib = _lib.load()
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
@@ -108,7 +109,7 @@ class BipartiteGraph(object):
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def from_id_edges(cls, ids_u, ids_b, device=None, build='host'):
+    def from_id_edges(cls, ids_u, ids_b, device=None, build='device'):
         ids_u = np.asarray(ids_u, dtype=np.int64)
         ids_b = np.asarray(ids_b, dtype=np.int64)
         users, eu = np.unique(ids_u, return_inverse=True)

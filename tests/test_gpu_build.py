@@ -24,7 +24,7 @@ def same_graph(a, b):
 def test_device_build_scores_match_host_build(mods, name, n_pairs):
     graph, synth = mods
     cfg, eu, eb, pu, pv = synth.make_config(name, n_pairs=n_pairs)
-    Gh = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    Gh = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, build='host')
     Gd = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, build='device')
     same_graph(Gh, Gd)
     a = Gh.score_pairs_host(pu, pv, want_hop2=True)
@@ -47,8 +47,18 @@ def test_device_build_small_and_odd_shapes(mods):
         got = G.score_pairs_host(pu, pv)
         want = c_oracle.score_pair_arrays(n_users, n_biz, eu, eb, pu, pv)
         check_against(got, want, pu.size)
-    with pytest.raises(ValueError):
-        graph.BipartiteGraph(4, 3, [0, 5], [0, 0], build='device')   # endpoint out of range
+    for build in ('host', 'device'):
+        with pytest.raises(ValueError):
+            graph.BipartiteGraph(4, 3, [0, 5], [0, 0], build=build)   # endpoint out of range
+    # the host builder on the same odd shapes
+    for n_users, n_biz, n_edges in ((1, 1, 1), (5, 3, 0), (3000, 2, 5000)):
+        eu = rng.integers(0, n_users, n_edges)
+        eb = rng.integers(0, n_biz, n_edges)
+        pu = rng.integers(-1, n_users, 300)
+        pv = rng.integers(-1, n_biz, 300)
+        G = graph.BipartiteGraph(n_users, n_biz, eu, eb, build='host')
+        check_against(G.score_pairs_host(pu, pv),
+                      c_oracle.score_pair_arrays(n_users, n_biz, eu, eb, pu, pv), pu.size)
 
 
 def test_device_build_c2_and_timing(mods):
@@ -57,7 +67,7 @@ def test_device_build_c2_and_timing(mods):
     graph, synth = mods
     cfg, eu, eb, pu, pv = synth.make_config('C2', n_pairs=200_000)
     t0 = time.perf_counter()
-    Gh = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    Gh = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, build='host')
     t_host = time.perf_counter() - t0
     deu, deb = torch.from_numpy(eu).cuda(), torch.from_numpy(eb).cuda()
     graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], deu, deb, build='device').close()   # warm-up
