@@ -400,12 +400,15 @@ class HostSession(object):
         hb[:] = pair_b
         return self.score_pinned(n)
 
-    def score_pinned(self, n, user_chunks=4):
+    def score_pinned(self, n, user_chunks=8, lead_chunks=1):
         """Score the first n pairs already sitting in the pinned input buffers.
 
-        Pipeline: H2D of the pair ids; business side over all pairs; then the user side in
-        `user_chunks` contiguous slices, each slice's results copied back on the copy stream
-        while the next slice is being scored -- only the last slice's D2H is exposed.
+        The pipeline is bound by the copy-back (56 B per pair over PCIe), so it is arranged to
+        start that copy as early as possible and never let it idle: the pair ids of the first
+        `lead_chunks` user-side slices go up first and are scored at once (their results start
+        the D2H engine), the rest of the ids follow on a separate upload stream, then the business
+        side over all pairs (its 24 B/pair backlog keeps the D2H engine busy), then the remaining
+        user-side slices, each slice's copy-back overlapping the next slice's scoring.
         """
         n = int(n)
         if n > self.n_max:
@@ -416,31 +419,49 @@ class HostSession(object):
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
             copy = self.copy_stream
+            if getattr(self, 'up_stream', None) is None:
+                self.up_stream = torch.cuda.Stream(device=dev)
+            up = self.up_stream
             du, db = self.d_u[:n], self.d_b[:n]
-            du.copy_(self.h_u[:n], non_blocking=True)
-            db.copy_(self.h_b[:n], non_blocking=True)
-            ob = {k[2:]: self.d_out[k][:n] for k in bkeys}
-            g.score_side(_lib.SIDE_BUSINESS, du, db, out=ob)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            with torch.cuda.stream(copy):
-                copy.wait_event(ev)
-                for k in bkeys:
-                    self.h_out[k][:n].copy_(self.d_out[k][:n], non_blocking=True)
             chunks = max(1, min(int(user_chunks), n // 65536 or 1))
             bounds = [(n * c) // chunks for c in range(chunks + 1)]
-            for c in range(chunks):
-                lo, hi = bounds[c], bounds[c + 1]
-                if hi <= lo:
-                    continue
-                ou = {(k[2:] if k.startswith('u_') else k): self.d_out[k][lo:hi] for k in ukeys}
-                g.score_side(_lib.SIDE_USER, du[lo:hi], db[lo:hi], want_pa=True, out=ou)
+            lead = max(0, min(int(lead_chunks), chunks - 1))
+            head = bounds[lead]
+            # upload: the head on the main stream, the rest beside it
+            if head:
+                du[:head].copy_(self.h_u[:head], non_blocking=True)
+                db[:head].copy_(self.h_b[:head], non_blocking=True)
+            up.wait_stream(main)
+            with torch.cuda.stream(up):
+                du[head:].copy_(self.h_u[head:n], non_blocking=True)
+                db[head:].copy_(self.h_b[head:n], non_blocking=True)
+                ev_up = torch.cuda.Event()
+                ev_up.record(up)
+
+            def copy_back(names, lo, hi):
                 ev = torch.cuda.Event()
                 ev.record(main)
                 with torch.cuda.stream(copy):
                     copy.wait_event(ev)
-                    for k in ukeys:
+                    for k in names:
                         self.h_out[k][lo:hi].copy_(self.d_out[k][lo:hi], non_blocking=True)
+
+            def user_slice(c):
+                lo, hi = bounds[c], bounds[c + 1]
+                if hi <= lo:
+                    return
+                ou = {(k[2:] if k.startswith('u_') else k): self.d_out[k][lo:hi] for k in ukeys}
+                g.score_side(_lib.SIDE_USER, du[lo:hi], db[lo:hi], want_pa=True, out=ou)
+                copy_back(ukeys, lo, hi)
+
+            for c in range(lead):
+                user_slice(c)
+            main.wait_event(ev_up)
+            ob = {k[2:]: self.d_out[k][:n] for k in bkeys}
+            g.score_side(_lib.SIDE_BUSINESS, du, db, out=ob)
+            copy_back(bkeys, 0, n)
+            for c in range(lead, chunks):
+                user_slice(c)
             main.wait_stream(copy)
             main.synchronize()
         return {k: self.h_out[k][:n].numpy() for k in self.KEYS}

@@ -115,13 +115,13 @@ def test_host_session_matches_plain_path(mods):
     G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
     want = G.score_pairs_host(pu, pv)
     sess = G.host_session(pu.size + 10)
-    for chunks in (1, 4):
+    for chunks, lead in ((1, 0), (1, 1), (4, 0), (8, 1), (8, 3), (16, 20)):
         hu, hb = sess.pinned_inputs(pu.size)
         hu[:] = pu
         hb[:] = pv
-        got = sess.score_pinned(pu.size, user_chunks=chunks)
+        got = sess.score_pinned(pu.size, user_chunks=chunks, lead_chunks=lead)
         for k in want:
-            assert np.array_equal(got[k], want[k]), (chunks, k)
+            assert np.array_equal(got[k], want[k]), (chunks, lead, k)
     got = sess.score(pu[:777], pv[:777])
     for k in want:
         assert np.array_equal(got[k], want[k][:777]), k
