@@ -66,11 +66,10 @@ struct SideArgs {
     const int* __restrict__ item_start;
     const int* __restrict__ item_end;
     const int* __restrict__ n_items;
-    const int* __restrict__ perm;           // caller-order pair index per grouped position, or
-                                            // null when the grouped order IS the caller order
-    const int* __restrict__ gpartner;       // partner y of every pair, grouped order
-    const int* __restrict__ mode;           // MODE_RUNS: grouped order == caller order (perm and
-    const int* __restrict__ caller_y;       //            gpartner are unused; partners = caller_y)
+    const int2* __restrict__ pg;            // sort mode: (caller-order pair index, partner y) per
+                                            // grouped position -- one 8-byte scattered store
+    const int* __restrict__ mode;           // MODE_RUNS: grouped order == caller order, pg is
+    const int* __restrict__ caller_y;       //            unused and the partners are caller_y
     int* work_counter;
     // sort mode only: results are first written as 24-byte records in GROUPED order (coalesced)
     // and brought to the caller's order by k_unpermute; null = write the outputs directly
@@ -287,15 +286,14 @@ __global__ void __launch_bounds__(1024) k_group_scan(const int* __restrict__ mod
 
 __global__ void k_group_scatter(const int* __restrict__ mode, const int* __restrict__ keys,
                                 const int* __restrict__ gy, long long n,
-                                unsigned* __restrict__ cursor, int* __restrict__ perm,
-                                int* __restrict__ gpartner, int* __restrict__ inv) {
+                                unsigned* __restrict__ cursor, int2* __restrict__ pg,
+                                int* __restrict__ inv) {
     if (*mode != MODE_SORT) return;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         const unsigned pos = atomicAdd(&cursor[keys[i]], 1u);   // cursor starts at the group offset
-        perm[pos] = (int)i;
-        gpartner[pos] = gy[i];
+        pg[pos] = make_int2((int)i, gy[i]);
         inv[i] = (int)pos;
     }
 }
@@ -653,6 +651,11 @@ __device__ __forceinline__ void stage2(const SideArgs& a, GroupRegs& g) {
     g.xrow = g.x < a.n_side ? a.g_row[g.x] : 0ull;
 }
 
+// (caller-order index, partner) of the pair at grouped position k
+__device__ __forceinline__ int2 pair_at(const SideArgs& a, long long k) {
+    return a.pg ? a.pg[k] : make_int2((int)k, a.caller_y[k]);
+}
+
 template <int NT, bool RANGED, bool REC>
 __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREADS_PER_SM / NT) : 1)
     k_score_side(SideArgs a) {
@@ -662,8 +665,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_items = *a.n_items;
     if (*a.mode == MODE_RUNS) {   // kernel parameters are per-thread copies: patch them locally
-        a.perm = nullptr;
-        a.gpartner = a.caller_y;
+        a.pg = nullptr;
     }
 
 #ifdef BLP_PHASE_TIMING
@@ -699,7 +701,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         if (x >= a.n_side) {
             // pairs with an id that is not in the graph: every score is the literal 0
             for (long long k = p0 + tid; k < p1; k += NT) {
-                int idx = a.perm ? a.perm[k] : (int)k;
+                int idx = a.pg ? a.pg[k].x : (int)k;
                 if (REC) {
                     a.rec[3 * k] = a.rec[3 * k + 1] = a.rec[3 * k + 2] = 0ull;
                 } else {
@@ -731,8 +733,9 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         unsigned long long park_row = 0ull;
         int park_idx = 0;
         if (tid < kTile && p0 + tid < p1) {
-            park_row = a.m_row[a.gpartner[p0 + tid]];
-            park_idx = a.perm ? a.perm[p0 + tid] : (int)(p0 + tid);
+            const int2 iy = pair_at(a, p0 + tid);
+            park_row = a.m_row[iy.y];
+            park_idx = iy.x;
         }
 
         const int n_ranges = RANGED ? a.n_ranges : 1;
@@ -859,9 +862,15 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             int nch = 0;
             if (tid < count) {
                 const bool first = tb == p0 && pass == 0;
-                unsigned long long row = first ? ts.aa[tid] : a.m_row[a.gpartner[tb + tid]];
+                unsigned long long row;
+                if (first) {
+                    row = ts.aa[tid];
+                } else {
+                    const int2 iy = pair_at(a, tb + tid);
+                    row = a.m_row[iy.y];
+                    ts.idx[tid] = iy.x;
+                }
                 ts.row[tid] = row;
-                if (!first) ts.idx[tid] = a.perm ? a.perm[tb + tid] : (int)(tb + tid);
                 ts.cn[tid] = 0;
                 ts.aa[tid] = 0ull;
                 nch = long_chunks(row);
@@ -1151,7 +1160,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     }
     if (force != MODE_RUNS) {
         unsigned *cnt = nullptr, *grp_off = nullptr;
-        int *perm = nullptr, *gpartner = nullptr;
+        int2* pg = nullptr;
         BLP_TRY_SCRATCH(alloc((void**)&inv, sizeof(int) * (size_t)n));
         // grouped-order result records + gather pass: only when the sort mode is certain (the
         // business side); a list whose mode is decided on the device writes its outputs directly
@@ -1159,19 +1168,17 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
             BLP_TRY_SCRATCH(alloc((void**)&a.rec, sizeof(unsigned long long) * 3 * (size_t)n));
         BLP_TRY_SCRATCH(alloc((void**)&cnt, sizeof(unsigned) * (size_t)n_keys));
         BLP_TRY_SCRATCH(alloc((void**)&grp_off, sizeof(unsigned) * (size_t)n_keys));
-        BLP_TRY_SCRATCH(alloc((void**)&perm, sizeof(int) * (size_t)n));
-        BLP_TRY_SCRATCH(alloc((void**)&gpartner, sizeof(int) * (size_t)n));
+        BLP_TRY_SCRATCH(alloc((void**)&pg, sizeof(int2) * (size_t)n));
         BLP_TRY_SCRATCH(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
         k_group_count<<<gblocks, 256, 0, st>>>(mode, keys, n, cnt);
         BLP_TRY_SCRATCH(cudaGetLastError());
         k_group_scan<<<1, 1024, 0, st>>>(mode, cnt, n_keys, grp_off, item_key, item_start,
                                          item_end, scalars);
         BLP_TRY_SCRATCH(cudaGetLastError());
-        k_group_scatter<<<gblocks, 256, 0, st>>>(mode, keys, gy, n, grp_off, perm, gpartner, inv);
+        k_group_scatter<<<gblocks, 256, 0, st>>>(mode, keys, gy, n, grp_off, pg, inv);
         BLP_TRY_SCRATCH(cudaGetLastError());
         launches += 3;
-        a.perm = perm;
-        a.gpartner = gpartner;
+        a.pg = pg;
     }
     a.mode = mode;
     a.caller_y = gy;
