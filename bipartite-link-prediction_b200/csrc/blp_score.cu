@@ -1096,10 +1096,24 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     // ---- stream-ordered scratch + grouping
     const int n_keys = a.n_side + 1;
     std::vector<void*> scratch;
+    // one stream-ordered block for all scratch of the call (an idle GPU would otherwise wait for
+    // a dozen allocator calls before the first kernel): carved by a bump pointer, 256-byte aligned
+    const size_t n_sz = (size_t)n, k_sz = (size_t)n_keys, i_sz = std::max(n_sz, k_sz);
+    const size_t arena_bytes = 4 * n_sz + 12 * i_sz + 8 * k_sz + 12 * n_sz + 24 * n_sz +
+                               (ranged ? 12 * n_sz : 0) + 64 * 256;
+    unsigned char* arena = nullptr;
+    size_t arena_used = 0;
+    {
+        cudaError_t e = cudaMallocAsync((void**)&arena, arena_bytes, st);
+        if (e != cudaSuccess) return blp::cuda_fail(e, "cudaMallocAsync(scratch)", __FILE__, __LINE__);
+        scratch.push_back(arena);
+    }
     auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
-        cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, st);
-        if (e == cudaSuccess) scratch.push_back(*p);
-        return e;
+        const size_t at = (arena_used + 255) & ~(size_t)255;
+        if (at + bytes > arena_bytes) return cudaErrorMemoryAllocation;   // sizing bug, not OOM
+        *p = arena + at;
+        arena_used = at + bytes;
+        return cudaSuccess;
     };
     auto release = [&]() {
         for (void* p : scratch) cudaFreeAsync(p, st);
