@@ -18,6 +18,9 @@ struct blp_graph {
     int sm_count = 0;
     int max_smem_optin = 0;  // bytes of dynamic shared memory one CTA may opt in to
     int reserve_sms = 0;     // SMs left out of the persistent scoring grids
+    // CTAs per SM of the scoring-kernel variants already configured: [nt 256/512/1024][ranged][rec]
+    int occ_cache[3][2][2] = {};
+    size_t occ_smem[3][2][2] = {};
     int32_t n_users = 0, n_biz = 0;
     int64_t n_edges_in = 0, n_edges = 0;
     int32_t n_users_in = 0, n_biz_in = 0, max_udeg = 0, max_bdeg = 0;

@@ -933,8 +933,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
 
 template <int NT, bool RANGED, bool REC>
 static int launch_side(const SideArgs& a, int grid, size_t smem, cudaStream_t st) {
-    BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_side<NT, RANGED, REC>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (the dynamic shared-memory opt-in for this size was made by occupancy<>() and is cached)
     k_score_side<NT, RANGED, REC><<<grid, NT, smem, st>>>(a);
     BLP_CUDA_TRY(cudaGetLastError());
     return BLP_OK;
@@ -1215,10 +1214,22 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     else nt = 1024;
     const int use_sms = std::max(1, g->sm_count - g->reserve_sms);
     const bool rec_mode = a.rec != nullptr;
+    // the occupancy query and the shared-memory opt-in are done once per variant and size
+    const int nt_i = nt == 256 ? 0 : (nt == 512 ? 1 : 2);
+    int& occ_slot = g->occ_cache[nt_i][ranged ? 1 : 0][rec_mode ? 1 : 0];
+    size_t& occ_smem = g->occ_smem[nt_i][ranged ? 1 : 0][rec_mode ? 1 : 0];
 #define BLP_DISPATCH(NTV, RV)                                               \
     do {                                                                    \
-        rc = rec_mode ? occupancy<NTV, RV, true>(smem, &per_sm)             \
-                      : occupancy<NTV, RV, false>(smem, &per_sm);           \
+        if (occ_slot > 0 && occ_smem == smem) {                             \
+            per_sm = occ_slot;                                              \
+        } else {                                                            \
+            rc = rec_mode ? occupancy<NTV, RV, true>(smem, &per_sm)         \
+                          : occupancy<NTV, RV, false>(smem, &per_sm);       \
+            if (rc == BLP_OK) {                                             \
+                occ_slot = per_sm;                                          \
+                occ_smem = smem;                                            \
+            }                                                               \
+        }                                                                   \
         if (rc == BLP_OK && per_sm < 1) {                                   \
             set_error("blp_score_pairs: scoring kernel does not fit on an SM"); \
             rc = BLP_ERR_UNSUPPORTED;                                       \
