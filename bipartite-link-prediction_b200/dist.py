@@ -165,6 +165,7 @@ def score_and_gather_overlapped(graph, d_u, d_b, chunks=4, dst=0, group=None, ou
     with torch.cuda.stream(side):
         graph.score_side(_lib.SIDE_BUSINESS, d_u, d_b, out={k[2:]: out[k] for k in bkeys},
                          stream=side)
+    gather_async(bkeys, 0, n, side)      # queued first: it is the largest transfer
     # ... and the user side slice by slice, each slice's gather behind the next slice's scoring
     for c in range(chunks):
         lo, hi = bounds[c], bounds[c + 1]
@@ -173,7 +174,6 @@ def score_and_gather_overlapped(graph, d_u, d_b, chunks=4, dst=0, group=None, ou
         ou = {(k[2:] if k.startswith('u_') else k): out[k][lo:hi] for k in ukeys}
         graph.score_side(_lib.SIDE_USER, d_u[lo:hi], d_b[lo:hi], want_pa=True, out=ou)
         gather_async(ukeys, lo, hi, main)
-    gather_async(bkeys, 0, n, side)
     main.wait_stream(side)
     graph.reserve_sms(0)
     main.wait_stream(comm)
