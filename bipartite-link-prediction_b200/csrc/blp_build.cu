@@ -553,6 +553,8 @@ extern "C" int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n
         return e;
     };
     int* tmp = nullptr;
+    g->u_adj_len = (int64_t)u_len;
+    g->b_adj_len = (int64_t)b_len;
     BLP_TRY_B(keep((void**)&g->u_adj, sizeof(int) * (size_t)u_len));
     BLP_TRY_B(keep((void**)&g->b_adj, sizeof(int) * (size_t)b_len));
     BLP_TRY_B(keep((void**)&g->u_adjw, sizeof(unsigned) * (size_t)u_len));

@@ -282,6 +282,8 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
             blp::set_error("blp_graph_create: graph too large for the packed row descriptors");
             return BLP_ERR_UNSUPPORTED;
         }
+        g->u_adj_len = u_off[n_users];
+        g->b_adj_len = b_off[n_biz];
         std::vector<unsigned long long> u_row((size_t)n_users), b_row((size_t)n_biz);
         for (int32_t u = 0; u < n_users; ++u)
             u_row[u] = ((unsigned long long)(u_off[u] >> 2) << 24) | (unsigned)u_deg[u];
@@ -330,6 +332,8 @@ extern "C" int blp_graph_destroy(blp_graph* g) {
     for (int sd = 0; sd < 2; ++sd) {
         cudaFree(g->xrow[sd]);
         cudaFree(g->hub_bm[sd]);
+        cudaFree(g->node_wt[sd]);
+        cudaFree(g->light[sd]);
     }
     for (int sd = 0; sd < 2; ++sd)
         for (int k = 0; k < 3; ++k)

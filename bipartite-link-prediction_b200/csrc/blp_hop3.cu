@@ -19,7 +19,7 @@ constexpr unsigned kAll = 0xffffffffu;
 
 __device__ __forceinline__ int h3_deg(unsigned long long row) { return (int)(row & 0xffffffull); }
 __device__ __forceinline__ const int* h3_list(const int* adj, unsigned long long row) {
-    return adj + (long long)(row >> 24) * 4;
+    return adj + (long long)((row >> 24) & ((1ull << BLP_ROW_FIRST4_BITS) - 1)) * 4;
 }
 
 struct Hop3Args {

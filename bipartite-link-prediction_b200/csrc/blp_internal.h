@@ -9,6 +9,11 @@
 
 #include "blp.h"
 
+// Packed row descriptor fields (see blp_graph below).
+#define BLP_ROW_FIRST4_BITS 28
+#define BLP_ROW_SLOT_SHIFT 52
+#define BLP_ROW_MAX_SLOTS 2047
+
 // Fixed point for the Adamic-Adar weights: integer sums are order independent.  A weight is at
 // most 1/ln 2 = 1.4427 < 2, so Q1.31 fits 32 bits; sums are kept in 64 bits.
 #define BLP_AA_FRAC_BITS 31
@@ -25,10 +30,13 @@ struct blp_graph {
     int64_t n_edges_in = 0, n_edges = 0;
     int32_t n_users_in = 0, n_biz_in = 0, max_udeg = 0, max_bdeg = 0;
     int64_t device_bytes = 0;
+    int64_t u_adj_len = 0, b_adj_len = 0;   // padded entries of u_adj / b_adj
     // Both CSR directions.  Every row is padded to a multiple of
     // four ids with the sentinel n_biz (user rows) / n_users (business rows), so every row starts
     // 16-byte aligned and is read with 128-bit loads without a tail.
     // Row descriptors: (first padded entry / 4) << 24 | true degree -- one 8-byte load per list.
+    // Bits 52..62 hold (hub-bitmap slot + 1) of a node whose neighbour list is also kept as a
+    // bitmap (0 = none); they are set only when every first-entry index fits 28 bits.
     unsigned long long* u_row = nullptr;  // [n_users]
     unsigned long long* b_row = nullptr;  // [n_biz]
     int* u_adj = nullptr;        // user -> businesses, ascending
@@ -42,10 +50,19 @@ struct blp_graph {
     // Hub bitmaps.  For side s (0 = user side, 1 = business side) the middle nodes of degree >=
     // hub_min_deg[s] have their whole neighbour list precomputed as a bitmap over the grouping
     // side, so the two-hop expansion ORs 128-bit words instead of walking the list id by id.
+    // Middle nodes of degree >= probe_min_deg[s] (<= hub_min_deg[s]) get a bitmap as well, used only
+    // by the intersection phase: when hop2(x) is small it is kept as an id list and a pair whose
+    // partner has a bitmap is scored by probing that bitmap with the list instead of streaming N(y).
     unsigned long long* xrow[2] = {nullptr, nullptr};   // expansion-side row descriptors (hubs tagged)
     unsigned* hub_bm[2] = {nullptr, nullptr};     // [n_hubs][bm_words]
-    int hub_min_deg[2] = {0x7fffffff, 0x7fffffff};
-    int n_hubs[2] = {0, 0};
+    unsigned char* light[2] = {nullptr, nullptr}; // per grouping node of side s: warp-per-group kernel
+    int light_ctas_per_sm = 0;
+    unsigned* node_wt[2] = {nullptr, nullptr};    // Q1.31 1/ln(deg) per grouping-side node of side s
+    int hub_min_deg[2] = {0x7fffffff, 0x7fffffff};    // expansion ORs the bitmap from here on
+    int probe_min_deg[2] = {0x7fffffff, 0x7fffffff};  // a bitmap exists from here on
+    int n_hubs[2] = {0, 0};                           // bitmaps kept (both kinds)
+    int probe_ratio = 2;                              // probe when deg(y) >= ratio * |hop2(x)|
+    bool row_slots[2] = {false, false};               // slot bits present in the middle rows of side s
     blp_score_stats_t stats[2] = {};
     cudaEvent_t ev[2][3] = {};   // per side: start, after grouping, after scoring
     bool ev_recorded[2] = {false, false};

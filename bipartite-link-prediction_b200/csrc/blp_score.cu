@@ -52,6 +52,9 @@ struct SideArgs {
     const unsigned long long* __restrict__ m_xrow;
     const unsigned* __restrict__ hub_bm;
     int hub_words;                        // words per hub bitmap (whole id universe)
+    // probe path of the intersection: Q1.31 weight of every x-side node (null = path off)
+    const unsigned* __restrict__ node_wt;
+    int probe_ratio;
     // id-range passes: when the bitmap of the whole universe does not fit (or is not wanted) in
     // shared memory the group is processed n_ranges times, pass r covering ids
     // [r*range_bits, (r+1)*range_bits); partial cn / aa wait in scratch (grouped order)
@@ -66,6 +69,9 @@ struct SideArgs {
     const int* __restrict__ item_start;
     const int* __restrict__ item_end;
     const int* __restrict__ n_items;
+    // with the light / heavy split (k_split_items) each scoring kernel walks its own list of item
+    // indices: position i of the persistent loop is item item_list[i]; null = every item in order
+    const int* __restrict__ item_list;
     const int2* __restrict__ pg;            // sort mode: (caller-order pair index, partner y) per
                                             // grouped position -- one 8-byte scattered store
     const int* __restrict__ mode;           // MODE_RUNS: grouped order == caller order, pg is
@@ -92,7 +98,14 @@ __device__ __forceinline__ int4 ldg_stream(const int4* p) {
 }
 
 __device__ __forceinline__ int row_deg(unsigned long long row) { return (int)(row & 0xffffffull); }
-__device__ __forceinline__ long long row_first4(unsigned long long row) { return (long long)(row >> 24); }
+__device__ __forceinline__ long long row_first4(unsigned long long row) {
+    return (long long)((row >> 24) & ((1ull << BLP_ROW_FIRST4_BITS) - 1));
+}
+// hub-bitmap slot + 1 of the node the row belongs to (0 = its list has no bitmap); bit 63 is the
+// expansion-side hub flag of m_xrow and is not part of the field
+__device__ __forceinline__ int row_slot1(unsigned long long row) {
+    return (int)((row >> BLP_ROW_SLOT_SHIFT) & (unsigned long long)BLP_ROW_MAX_SLOTS);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Grouping.  Every pair gets a key: the node whose hop-2 set it needs, or n_side when an id of
@@ -321,6 +334,14 @@ __global__ void k_unpermute(const int* __restrict__ mode, const unsigned long lo
 // The scoring kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int kShortV4 = 4;   // lists of <= 16 ids take the sub-warp path (4 lanes per list)
+// Probe path.  A hop-2 set built from at most kProbeCap list entries and no hub bitmap is also
+// kept as an id list (the atomicOr that turns a bit on appends the id).  A pair of that group
+// whose partner y has a bitmap and deg(y) >= probe_ratio * |hop2(x)| is then scored by probing
+// y's bitmap with the list -- |hop2(x)| global loads instead of streaming deg(y) ids + weights.
+// On C2 this replaces ~45 % of all streamed ids by ~5 % as many probes (hub partners are drawn
+// in proportion to their degree; two thirds of the users have no hub business and a small set).
+constexpr int kProbeCap = 768;
+constexpr int kProbeRatio = 2;   // default; BLP_PROBE_RATIO overrides it at graph creation
 
 struct TileSmem {
     unsigned long long row[kTile];     // packed row descriptor of every list of the tile
@@ -330,13 +351,19 @@ struct TileSmem {
     int next_chunk[4];                 // dynamic chunk dispensers, one per sweep kind (OP_*)
     int cn[kTile];
     int idx[kTile];                    // caller-order pair index
-    int hub[kTile];                    // hub-bitmap slots met in the current expansion tile
+    int hub[kProbeCap];                // [0, kTile): hub-bitmap slots met in the current expansion
+                                       // tile; hub-free group: hop2(x) as an id list (probe path)
     int wsum[32];
     int red[32];
     int item_next;
     int hop2cnt;                       // bits turned on during the expansion of this group
     int nhub;
+    int list_on;                       // this group's expansion appends the ids it turns on to hub[]
+    int list_n;                        // ids in the list
+    int nprobe;                        // pairs of the current tile scored by probing
+    unsigned char probe[kTile];        // their tile positions
 };
+static_assert(kProbeCap >= kTile && kTile <= 256, "hub[] doubles as the list; probe[] holds uint8");
 
 // Exclusive scan of `v` over the first kTile threads into ts.scan[]; ts.scan[kTile] = total.
 template <int NT>
@@ -457,7 +484,8 @@ __device__ __forceinline__ void touch(unsigned* bm, int id, unsigned wt, unsigne
 
 template <int OP, bool RANGED>
 __device__ __forceinline__ void touch4(unsigned* bm, int4 v, uint4 wt, unsigned& cnt,
-                                       unsigned long long& acc, int n_side, int lo, int range_bits) {
+                                       unsigned long long& acc, int n_side, int lo, int range_bits,
+                                       TileSmem* list, int self) {
     if (OP == OP_SET) {
         // four probes first, then the atomics that are still needed, all in flight together
         const int id[4] = {v.x, v.y, v.z, v.w};
@@ -476,7 +504,12 @@ __device__ __forceinline__ void touch4(unsigned* bm, int4 v, uint4 wt, unsigned&
             if (need[k]) old[k] = atomicOr(bm + (rel[k] >> 5), bit[k]);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cnt += need[k] && !(old[k] & bit[k]);
+        for (int k = 0; k < 4; ++k) {
+            const bool turned_on = need[k] && !(old[k] & bit[k]);
+            cnt += turned_on;
+            if (!RANGED && list && turned_on && id[k] != self)   // hop2(x) excludes x
+                list->hub[atomicAdd(&list->list_n, 1)] = id[k];
+        }
         return;
     }
     touch<OP, RANGED>(bm, v.x, wt.x, cnt, acc, n_side, lo, range_bits);
@@ -490,8 +523,9 @@ __device__ __forceinline__ void touch4(unsigned* bm, int4 v, uint4 wt, unsigned&
 // 512-id chunks dealt round-robin to warps, so a hub list is spread over the whole CTA.
 template <int NT, int OP, bool RANGED>
 __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, TileSmem& ts,
-                                               int count, int lane, int warp, int lo) {
+                                               int count, int lane, int warp, int lo, int self) {
     unsigned set_total = 0;   // OP_SET: bits this thread turned on
+    TileSmem* const list = (OP == OP_SET && !RANGED && ts.list_on) ? &ts : nullptr;
     constexpr int NW = NT / 32;
     const int4* adj4 = reinterpret_cast<const int4*>(a.m_adj);
     const uint4* adjw4 = reinterpret_cast<const uint4*>(a.m_adjw);
@@ -513,7 +547,7 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
                 const long long at = row_first4(row) + sub;
                 int4 v = ldg_stream(adj4 + at);
                 uint4 wt = OP == OP_TEST ? ldg_stream_u(adjw4 + at) : zero4;
-                touch4<OP, RANGED>(bm, v, wt, cnt, acc, a.n_side, lo, a.range_bits);
+                touch4<OP, RANGED>(bm, v, wt, cnt, acc, a.n_side, lo, a.range_bits, list, self);
             }
             if (OP == OP_SET) set_total += cnt;
             if (OP == OP_TEST) {
@@ -526,6 +560,45 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
                 if (is_short && sub == 0) {
                     ts.cn[j] = (int)cnt;
                     ts.aa[j] = acc;
+                }
+            }
+        }
+    }
+    // ---- probe pairs: one warp per pair, the hop-2 id list against the partner's bitmap
+    if (OP == OP_TEST && !RANGED) {
+        const int np = ts.nprobe;
+        if (np > 0) {
+            const int nl = ts.list_n;
+            for (int q = warp; q < np; q += NW) {
+                const int j = ts.probe[q];
+                const unsigned* hb =
+                    a.hub_bm + (size_t)(row_slot1(ts.row[j]) - 1) * (size_t)a.hub_words;
+                unsigned cnt = 0;
+                unsigned long long acc = 0ull;
+                for (int i0 = lane; i0 < nl; i0 += 128) {
+                    int w[4];
+                    unsigned word[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)   // bit n_side is never on in a hub bitmap
+                        w[k] = i0 + 32 * k < nl ? ts.hub[i0 + 32 * k] : a.n_side;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) word[k] = __ldg(hb + (w[k] >> 5));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if ((word[k] >> (w[k] & 31)) & 1u) {
+                            ++cnt;
+                            acc += __ldg(a.node_wt + w[k]);
+                        }
+                }
+                cnt = __reduce_add_sync(kFull, cnt);
+                if (cnt > 0) {   // per-lane acc < 24 * 2^31: the two REDUX halves add it exactly
+                    const unsigned lo16 = __reduce_add_sync(kFull, (unsigned)(acc & 0xffffull));
+                    const unsigned hi = __reduce_add_sync(kFull, (unsigned)(acc >> 16));
+                    acc = ((unsigned long long)hi << 16) + lo16;
+                }
+                if (lane == 0) {
+                    ts.cn[j] = (int)cnt;
+                    ts.aa[j] = cnt > 0 ? acc : 0ull;
                 }
             }
         }
@@ -563,7 +636,8 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
                     if (32 * (2 * half + k) < n)
-                        touch4<OP, RANGED>(bm, v[k], wt[k], cnt, acc, a.n_side, lo, a.range_bits);
+                        touch4<OP, RANGED>(bm, v[k], wt[k], cnt, acc, a.n_side, lo, a.range_bits, list,
+                                           self);
             }
         }
         if (OP == OP_SET) set_total += cnt;
@@ -642,9 +716,10 @@ __device__ __forceinline__ void stage1(const SideArgs& a, GroupRegs& g, int n_it
     g.x = a.n_side + 1;
     g.p0 = g.p1 = 0;
     if (g.item < n_items) {
-        g.x = a.item_key[g.item];
-        g.p0 = a.item_start[g.item];
-        g.p1 = a.item_end[g.item];
+        const int it = a.item_list ? a.item_list[g.item] : g.item;
+        g.x = a.item_key[it];
+        g.p0 = a.item_start[it];
+        g.p1 = a.item_end[it];
     }
 }
 __device__ __forceinline__ void stage2(const SideArgs& a, GroupRegs& g) {
@@ -675,6 +750,9 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         ts.item_next = atomicAdd(a.work_counter, 1);
         ts.nhub = 0;
         ts.hop2cnt = 0;
+        ts.list_on = 0;
+        ts.list_n = 0;
+        ts.nprobe = 0;
     }
     {
         uint4* b4 = reinterpret_cast<uint4*>(bm);
@@ -748,16 +826,26 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         for (int tb = 0; tb < xdeg; tb += kTile) {
             const int count = min(kTile, xdeg - tb);
             int nch = 0;
+            int list_len = 0;
             if (tid < count) {
                 unsigned long long row = (tb == 0 && pass == 0) ? cur.rowx : a.m_xrow[xadj[tb + tid]];
+                list_len = min(row_deg(row), kProbeCap + 1);
                 if (row >> 63) {
                     const int h = atomicAdd(&ts.nhub, 1);
                     ts.hub[h] = (int)((row >> 24) & 0x7fffffffull);
                     ts.cn[h] = row_deg(row);   // ts.cn is idle during the expansion
                     row = 0ull;                // degree 0: skipped by both list walkers
+                    list_len = kProbeCap + 1;
                 }
                 ts.row[tid] = row;
                 nch = long_chunks(row);
+            }
+            if (!RANGED && tb == 0 && warp == 0) {
+                // probe path: keep hop2(x) as a list when x's whole expansion is this warp's, has
+                // no hub and walks at most kProbeCap ids (published by tile_scan's barrier)
+                const int walked = __reduce_add_sync(kFull, list_len);
+                if (lane == 0)
+                    ts.list_on = (a.node_wt != nullptr && xdeg <= 32 && walked <= kProbeCap) ? 1 : 0;
             }
             tile_scan<NT>(ts, nch, tid, count);
             if (pass == 0 && tb == 0) {            // stage 1 of the next group's descriptor
@@ -839,7 +927,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             }
             if (pass == 0 && tb == 0) stage2(a, nxt);
             BLP_TICK(2);
-            newbits += (int)sweep_tile<NT, OP_SET, RANGED>(a, bm, ts, count, lane, warp, lo);
+            newbits += (int)sweep_tile<NT, OP_SET, RANGED>(a, bm, ts, count, lane, warp, lo, x);
             newbits = __reduce_add_sync(kFull, newbits);
             if (lane == 0 && newbits != 0) atomicAdd(&ts.hop2cnt, newbits);
             __syncthreads();
@@ -850,6 +938,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         // ---- phase 2: x itself is in every N(m), so its bit is always on: |hop2(x)| = bits - 1
         // (with id ranges the count is complete once the last pass has expanded)
         const int hop2 = ts.hop2cnt - 1;
+        const bool probing = !RANGED && ts.list_on;   // then ts.hub[0 .. hop2) lists hop2(x)
         if (tid == 0) {   // ordered before the tests by tile_scan's barriers
             const unsigned rel = (unsigned)(x - lo);
             if (!RANGED || rel < (unsigned)a.range_bits) bm[rel >> 5] &= ~(1u << (rel & 31));
@@ -874,12 +963,17 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 ts.cn[tid] = 0;
                 ts.aa[tid] = 0ull;
                 nch = long_chunks(row);
+                if (probing && row_slot1(row) > 0 && (long long)a.probe_ratio * hop2 <= row_deg(row)) {
+                    ts.probe[atomicAdd(&ts.nprobe, 1)] = (unsigned char)tid;
+                    nch = 0;   // not streamed (a list this long is never on the short path)
+                }
             }
             tile_scan<NT>(ts, nch, tid, count);
             if (pass == 0 && tb == p0) stage4(a, nxt);
             BLP_TICK(6);
-            sweep_tile<NT, OP_TEST, RANGED>(a, bm, ts, count, lane, warp, lo);
+            sweep_tile<NT, OP_TEST, RANGED>(a, bm, ts, count, lane, warp, lo, x);
             __syncthreads();
+            if (!RANGED && tid == 0) ts.nprobe = 0;   // next use is behind the barrier below
             BLP_TICK(7);
             // epilogue: one thread per pair of the tile
             bool final_pass = true;
@@ -926,8 +1020,347 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         }   // id-range passes
-        if (tid == 0) ts.hop2cnt = 0;   // ordered before the next group's counting by its barriers
+        if (tid == 0) {   // ordered before the next group's counting by its barriers
+            ts.hop2cnt = 0;
+            ts.list_n = 0;
+        }
         cur = nxt;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Light groups: one WARP per group.
+//
+// Measured on C2 (tools/cost_model.py): 60 % of the CTA kernel's time is per-GROUP cost -- a
+// chain of ~8 CTA barriers and ~6 dependent global round trips per group with only four groups in
+// flight per SM (four 46 KB bitmaps) -- and about half of the groups are tiny: a user with a few
+// small businesses whose expansion walks a few hundred ids.  Such a group (flagged per node at
+// graph creation: <= 32 middle nodes, none of them an OR-hub, <= kLightCap ids walked) needs no
+// bitmap over the whole universe.  Here one warp owns it: hop2(x) goes into a 4 KB open-addressing
+// hash table in shared memory (and, in insertion order, into an id list), every partner list is
+// streamed against the table, and partners that have a bitmap are scored by probing it with the
+// list.  No CTA barrier anywhere, 32 groups in flight per SM instead of 4.  The arithmetic is the
+// same integer arithmetic as in k_score_side, so the outputs are bit-identical.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLightCap = 512;      // ids walked by the expansion of a light group, at most
+constexpr int kLightSlots = 1024;   // hash slots (load factor <= 0.5, typically ~0.2)
+constexpr int kLightWarps = 8;
+constexpr int kLightEmpty = -1;
+
+struct LightSmem {
+    int table[kLightSlots];
+    int list[kLightCap];
+};
+
+__device__ __forceinline__ unsigned light_hash(int id) {
+    return ((unsigned)id * 2654435761u) >> 22;   // 10 bits
+}
+static_assert(kLightSlots == 1024, "light_hash yields 10 bits");
+
+__device__ __forceinline__ bool light_has(const int* table, int id) {
+    unsigned s = light_hash(id);
+    while (true) {
+        const int v = table[s];
+        if (v == id) return true;
+        if (v == kLightEmpty) return false;   // also ends the search for the padding sentinel
+        s = (s + 1) & (kLightSlots - 1);
+    }
+}
+
+// true when THIS call put the id into the table
+__device__ __forceinline__ bool light_insert(int* table, int id) {
+    unsigned s = light_hash(id);
+    while (true) {
+        const int prev = atomicCAS(&table[s], kLightEmpty, id);
+        if (prev == kLightEmpty) return true;
+        if (prev == id) return false;
+        s = (s + 1) & (kLightSlots - 1);
+    }
+}
+
+// expansion step for the four ids of one 128-bit load; new ids are appended to the list with one
+// ballot per component (list_n is warp-uniform)
+__device__ __forceinline__ void light_expand4(LightSmem& ls, int4 v, bool active, int x, int n_side,
+                                              int& list_n, int lane) {
+    const int id[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool fresh = active && id[k] < n_side && id[k] != x && light_insert(ls.table, id[k]);
+        const unsigned m = __ballot_sync(kFull, fresh);
+        if (fresh) ls.list[list_n + __popc(m & ((1u << lane) - 1u))] = id[k];
+        list_n += __popc(m);
+    }
+}
+
+__device__ __forceinline__ void light_test4(const int* table, int4 v, uint4 wt, unsigned& cnt,
+                                            unsigned long long& acc) {
+    const int id[4] = {v.x, v.y, v.z, v.w};
+    const unsigned w[4] = {wt.x, wt.y, wt.z, wt.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (light_has(table, id[k])) {
+            ++cnt;
+            acc += w[k];
+        }
+}
+
+// exact warp sum of per-lane weight sums < 2^40 (three REDUX over 16-bit limbs would be needed
+// beyond that: a lane adds at most deg/32 + 4 weights of < 2^31)
+__device__ __forceinline__ unsigned long long light_sum64(unsigned long long acc) {
+    const unsigned l0 = __reduce_add_sync(kFull, (unsigned)(acc & 0xffffull));
+    const unsigned l1 = __reduce_add_sync(kFull, (unsigned)((acc >> 16) & 0xffffull));
+    const unsigned l2 = __reduce_add_sync(kFull, (unsigned)(acc >> 32));
+    return ((unsigned long long)l2 << 32) + ((unsigned long long)l1 << 16) + l0;
+}
+
+template <bool REC>
+__global__ void __launch_bounds__(kLightWarps * 32) k_score_light(SideArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    LightSmem& ls = reinterpret_cast<LightSmem*>(smem_raw)[warp];
+    const int n_items = *a.n_items;
+    if (*a.mode == MODE_RUNS) a.pg = nullptr;
+    const int4* adj4 = reinterpret_cast<const int4*>(a.m_adj);
+    const uint4* adjw4 = reinterpret_cast<const uint4*>(a.m_adjw);
+    {
+        int4* t4 = reinterpret_cast<int4*>(ls.table);
+        for (int i = lane; i < kLightSlots / 4; i += 32)
+            t4[i] = make_int4(kLightEmpty, kLightEmpty, kLightEmpty, kLightEmpty);
+    }
+    __syncwarp();
+    int c = 0;
+    if (lane == 0) c = atomicAdd(a.work_counter, 1);
+    c = __shfl_sync(kFull, c, 0);
+    while (c < n_items) {
+        int c_next = 0;
+        if (lane == 0) c_next = atomicAdd(a.work_counter, 1);   // latency hides behind this group
+        const int it = a.item_list[c];
+        const int x = a.item_key[it];
+        const long long p0 = a.item_start[it], p1 = a.item_end[it];
+        const unsigned long long xrow = a.g_row[x];
+        const int xdeg = row_deg(xrow);   // 1..32 by the light flag
+        // ---- expansion: every list N(m), m in N(x), into the table and the list
+        unsigned long long mrow = 0ull;
+        if (lane < xdeg) mrow = a.m_row[a.g_adj[row_first4(xrow) * 4 + lane]];
+        const int mn4 = (row_deg(mrow) + 3) >> 2;
+        int list_n = 0;
+        {
+            const int sub = lane & 3, slot = lane >> 2;
+            for (int base = 0; base < xdeg; base += 8) {
+                const unsigned long long r = __shfl_sync(kFull, mrow, min(base + slot, 31));
+                const int n4 = base + slot < xdeg ? (row_deg(r) + 3) >> 2 : 0;
+                const bool mine = n4 > 0 && n4 <= kShortV4 && sub < n4;
+                if (!__any_sync(kFull, mine)) continue;
+                int4 v = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
+                if (mine) v = ldg_stream(adj4 + row_first4(r) + sub);
+                light_expand4(ls, v, mine, x, a.n_side, list_n, lane);
+            }
+            unsigned longs = __ballot_sync(kFull, mn4 > kShortV4);
+            while (longs) {
+                const int j = __ffs(longs) - 1;
+                longs &= longs - 1;
+                const unsigned long long r = __shfl_sync(kFull, mrow, j);
+                const int n4 = (row_deg(r) + 3) >> 2;
+                const long long at = row_first4(r);
+                for (int i0 = 0; i0 < n4; i0 += 32) {
+                    const bool mine = i0 + lane < n4;
+                    int4 v = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
+                    if (mine) v = ldg_stream(adj4 + at + i0 + lane);
+                    light_expand4(ls, v, mine, x, a.n_side, list_n, lane);
+                }
+            }
+        }
+        __syncwarp();
+        const int hop2 = list_n;   // x itself was never inserted
+        // ---- the pairs of the group, 32 at a time: lane l owns pair tb + l
+        for (long long tb = p0; tb < p1; tb += 32) {
+            const int count = (int)min(32ll, p1 - tb);
+            unsigned long long row = 0ull;
+            int idx = 0;
+            if (lane < count) {
+                const int2 iy = pair_at(a, tb + lane);
+                row = a.m_row[iy.y];
+                idx = iy.x;
+            }
+            const int pdeg = row_deg(row);
+            const int pn4 = (pdeg + 3) >> 2;
+            const bool by_probe = lane < count && a.node_wt != nullptr && row_slot1(row) > 0 &&
+                                  (long long)a.probe_ratio * hop2 <= pdeg;
+            unsigned my_cn = 0;
+            unsigned long long my_aa = 0ull;
+            // short partner lists: 4 lanes per list, 8 lists per pass
+            {
+                const int sub = lane & 3, slot = lane >> 2;
+                for (int base = 0; base < count; base += 8) {
+                    const unsigned long long r = __shfl_sync(kFull, row, min(base + slot, 31));
+                    const int n4 = base + slot < count ? (row_deg(r) + 3) >> 2 : 0;
+                    const bool mine = n4 > 0 && n4 <= kShortV4 && sub < n4;
+                    if (!__any_sync(kFull, mine)) continue;
+                    unsigned cnt = 0;
+                    unsigned long long acc = 0ull;
+                    if (mine && hop2 > 0) {
+                        const long long at = row_first4(r) + sub;
+                        light_test4(ls.table, ldg_stream(adj4 + at), ldg_stream_u(adjw4 + at), cnt, acc);
+                    }
+                    cnt += __shfl_xor_sync(kFull, cnt, 1);
+                    cnt += __shfl_xor_sync(kFull, cnt, 2);
+                    acc += __shfl_xor_sync(kFull, acc, 1);
+                    acc += __shfl_xor_sync(kFull, acc, 2);
+                    // the result of list base + s sits in lanes 4s..4s+3; its owner is lane base + s
+                    const int src = ((lane - base) & 7) * 4;
+                    const unsigned got_c = __shfl_sync(kFull, cnt, src);
+                    const unsigned long long got_a = __shfl_sync(kFull, acc, src);
+                    if (lane >= base && lane < base + 8 && pn4 > 0 && pn4 <= kShortV4) {
+                        my_cn = got_c;
+                        my_aa = got_a;
+                    }
+                }
+            }
+            // partners with a bitmap: the hop-2 list against the bitmap
+            unsigned todo = __ballot_sync(kFull, by_probe);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const unsigned long long r = __shfl_sync(kFull, row, j);
+                const unsigned* hb = a.hub_bm + (size_t)(row_slot1(r) - 1) * (size_t)a.hub_words;
+                unsigned cnt = 0;
+                unsigned long long acc = 0ull;
+                for (int i0 = lane; i0 < hop2; i0 += 128) {
+                    int w[4];
+                    unsigned word[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)   // bit n_side is never on in a hub bitmap
+                        w[k] = i0 + 32 * k < hop2 ? ls.list[i0 + 32 * k] : a.n_side;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) word[k] = __ldg(hb + (w[k] >> 5));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if ((word[k] >> (w[k] & 31)) & 1u) {
+                            ++cnt;
+                            acc += __ldg(a.node_wt + w[k]);
+                        }
+                }
+                cnt = __reduce_add_sync(kFull, cnt);
+                if (cnt > 0) acc = light_sum64(acc);
+                if (lane == j) {
+                    my_cn = cnt;
+                    my_aa = cnt > 0 ? acc : 0ull;
+                }
+            }
+            // every other partner list: streamed by the whole warp against the table
+            todo = __ballot_sync(kFull, lane < count && pn4 > kShortV4 && !by_probe);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const unsigned long long r = __shfl_sync(kFull, row, j);
+                const int n4 = (row_deg(r) + 3) >> 2;
+                const long long at = row_first4(r);
+                unsigned cnt = 0;
+                unsigned long long acc = 0ull;
+                if (hop2 > 0) {
+                    for (int i0 = lane; i0 < n4; i0 += 64) {
+                        const bool second = i0 + 32 < n4;
+                        const int4 v0 = ldg_stream(adj4 + at + i0);
+                        const uint4 w0 = ldg_stream_u(adjw4 + at + i0);
+                        int4 v1 = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
+                        uint4 w1 = make_uint4(0u, 0u, 0u, 0u);
+                        if (second) {
+                            v1 = ldg_stream(adj4 + at + i0 + 32);
+                            w1 = ldg_stream_u(adjw4 + at + i0 + 32);
+                        }
+                        light_test4(ls.table, v0, w0, cnt, acc);
+                        if (second) light_test4(ls.table, v1, w1, cnt, acc);
+                    }
+                }
+                cnt = __reduce_add_sync(kFull, cnt);
+                if (cnt > 0) acc = light_sum64(acc);
+                if (lane == j) {
+                    my_cn = cnt;
+                    my_aa = cnt > 0 ? acc : 0ull;
+                }
+            }
+            // epilogue: same expressions as k_score_side
+            if (lane < count) {
+                const int cnn = (int)my_cn;
+                const int u = hop2 + pdeg - cnn;   // |a| + |b| - |a & b|  (similarity.py:110)
+                const double jv = __ddiv_rn((double)cnn, (double)u);
+                const double av = (double)my_aa * (1.0 / (double)(1ull << BLP_AA_FRAC_BITS));
+                if (REC) {
+                    unsigned long long* rr = a.rec + 3 * (tb + lane);
+                    rr[0] = (unsigned long long)(unsigned)cnn | ((unsigned long long)(unsigned)u << 32);
+                    rr[1] = (unsigned long long)__double_as_longlong(jv);
+                    rr[2] = (unsigned long long)__double_as_longlong(av);
+                } else {
+                    if (a.cn) a.cn[idx] = cnn;
+                    if (a.uni) a.uni[idx] = u;
+                    if (a.jac) a.jac[idx] = jv;
+                    if (a.aa) a.aa[idx] = av;
+                }
+                if (a.pa) a.pa[idx] = (long long)xdeg * (long long)pdeg;
+                if (a.hop2) a.hop2[idx] = hop2;
+            }
+        }
+        // leave the table empty for the next group
+        __syncwarp();
+        if (hop2 > 0) {
+            int4* t4 = reinterpret_cast<int4*>(ls.table);
+            for (int i = lane; i < kLightSlots / 4; i += 32)
+                t4[i] = make_int4(kLightEmpty, kLightEmpty, kLightEmpty, kLightEmpty);
+        }
+        __syncwarp();
+        c = __shfl_sync(kFull, c_next, 0);
+    }
+}
+
+// Per node of the grouping side: can its group go to k_score_light?  (run once per graph)
+__global__ void k_flag_light(int n_side, const unsigned long long* __restrict__ g_row,
+                             const int* __restrict__ g_adj,
+                             const unsigned long long* __restrict__ m_xrow,
+                             unsigned char* __restrict__ light) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n_side) return;
+    const unsigned long long xr = g_row[x];
+    const int d = row_deg(xr);
+    bool ok = d >= 1 && d <= 32;
+    long long walked = 0;
+    if (ok) {
+        const int* adj = g_adj + row_first4(xr) * 4;
+        for (int i = 0; i < d; ++i) {
+            const unsigned long long r = m_xrow[adj[i]];
+            if (r >> 63) ok = false;   // the expansion ORs a hub bitmap for this one
+            walked += row_deg(r);
+        }
+    }
+    light[x] = (ok && walked <= kLightCap) ? 1 : 0;
+}
+
+// Items -> two lists of item indices (light groups / everything else), order irrelevant.
+__global__ void k_split_items(const int* __restrict__ n_items, const int* __restrict__ item_key,
+                              const unsigned char* __restrict__ light, int n_side,
+                              int* __restrict__ light_list, int* __restrict__ heavy_list,
+                              int* __restrict__ counts /* [0] light, [1] heavy */) {
+    const int n = *n_items;
+    const int lane = threadIdx.x & 31;
+    const int stride = gridDim.x * blockDim.x;
+    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += stride) {
+        const int i = base + lane;
+        int cls = -1;
+        if (i < n) {
+            const int key = item_key[i];
+            cls = (key < n_side && light[key]) ? 0 : 1;
+        }
+        const unsigned ml = __ballot_sync(kFull, cls == 0), mh = __ballot_sync(kFull, cls == 1);
+        int bl = 0, bh = 0;
+        if (lane == 0) {
+            if (ml) bl = atomicAdd(&counts[0], __popc(ml));
+            if (mh) bh = atomicAdd(&counts[1], __popc(mh));
+        }
+        bl = __shfl_sync(kFull, bl, 0);
+        bh = __shfl_sync(kFull, bh, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (cls == 0) light_list[bl + __popc(ml & lt)] = i;
+        if (cls == 1) heavy_list[bh + __popc(mh & lt)] = i;
     }
 }
 
@@ -980,27 +1413,64 @@ int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host
         const long long bm_bytes = (long long)words * 4;
         int min_deg = (int)std::max<long long>(64, bm_bytes / 30);
         if (const char* e = getenv("BLP_HUB_MIN_DEG")) min_deg = atoi(e);   // tuning override
+        // Bitmaps used only by the intersection's probe path start lower: a probe costs about as
+        // much as a streamed id, and the path is taken when deg(y) >= kProbeRatio * |hop2(x)|
+        // with |hop2(x)| <= kProbeCap, so a bitmap pays off from a few hundred ids on.
+        int probe_deg = min_deg > 0 ? std::max(64, min_deg / 3) : 0;
+        if (const char* e = getenv("BLP_PROBE_MIN_DEG")) probe_deg = atoi(e);   // 0 = path off
+        // the slot field needs every first-entry index to fit BLP_ROW_FIRST4_BITS
+        const long long mid_entries = us ? g->b_adj_len : g->u_adj_len;
+        const bool slots_fit = mid_entries / 4 < (1LL << BLP_ROW_FIRST4_BITS);
+        if (probe_deg <= 0 || !slots_fit) probe_deg = 0;
+        else probe_deg = std::max(64, min_deg > 0 ? std::min(probe_deg, min_deg) : probe_deg);
+        const int any_deg = probe_deg > 0 ? probe_deg : min_deg;   // a bitmap exists from here on
         std::vector<int> hubs;
-        if (min_deg > 0)
+        if (any_deg > 0)
             for (int m = 0; m < n_mid; ++m)
-                if (mdeg[m] >= min_deg) hubs.push_back(m);
-        // budget: at most 4096 hubs and 2 GiB per side; keep the largest
-        size_t cap = (size_t)std::min<long long>(4096, (2LL << 30) / bm_bytes);
+                if (mdeg[m] >= any_deg) hubs.push_back(m);
+        // budget: at most BLP_ROW_MAX_SLOTS bitmaps and 2 GiB per side; keep the largest
+        size_t cap = (size_t)std::min<long long>(BLP_ROW_MAX_SLOTS, (2LL << 30) / bm_bytes);
         if (hubs.size() > cap) {
             std::sort(hubs.begin(), hubs.end(), [&](int a, int b) { return mdeg[a] > mdeg[b]; });
             hubs.resize(cap);
             std::sort(hubs.begin(), hubs.end());
         }
         g->n_hubs[side] = (int)hubs.size();
-        g->hub_min_deg[side] = min_deg;
+        g->hub_min_deg[side] = min_deg > 0 ? min_deg : 0x7fffffff;
+        g->probe_min_deg[side] = any_deg > 0 ? any_deg : 0x7fffffff;
         if (hubs.empty()) continue;
+        const bool probing = probe_deg > 0;
         // expansion-side descriptors: a copy of the middle rows with the hubs' entries replaced
         const unsigned long long* d_mrow = (const unsigned long long*)(us ? g->b_row : g->u_row);
         std::vector<unsigned long long> xrow((size_t)n_mid);
         BLP_CUDA_TRY(cudaMemcpy(xrow.data(), d_mrow, sizeof(unsigned long long) * (size_t)n_mid,
                                 cudaMemcpyDeviceToHost));
-        for (size_t h = 0; h < hubs.size(); ++h)
-            xrow[hubs[h]] = (1ull << 63) | ((unsigned long long)h << 24) | (unsigned)mdeg[hubs[h]];
+        // the middle rows themselves learn which of them has a bitmap (read by the intersection)
+        std::vector<unsigned long long> mrow;
+        if (probing) mrow = xrow;
+        for (size_t h = 0; h < hubs.size(); ++h) {
+            if (probing) mrow[hubs[h]] |= (unsigned long long)(h + 1) << BLP_ROW_SLOT_SHIFT;
+            if (min_deg > 0 && mdeg[hubs[h]] >= min_deg)   // the expansion ORs this one
+                xrow[hubs[h]] = (1ull << 63) | ((unsigned long long)h << 24) | (unsigned)mdeg[hubs[h]];
+        }
+        if (probing) {
+            BLP_CUDA_TRY(cudaMemcpy(const_cast<unsigned long long*>(d_mrow), mrow.data(),
+                                    sizeof(unsigned long long) * (size_t)n_mid,
+                                    cudaMemcpyHostToDevice));
+            // Q1.31 weight of every grouping-side node: a probe hit adds the weight of the id
+            const int* gdeg = us ? u_deg_host : b_deg_host;
+            std::vector<unsigned> lut;
+            weight_lut(us ? g->max_udeg : g->max_bdeg, lut);
+            std::vector<unsigned> wt((size_t)n_side + 1, 0u);
+            for (int i = 0; i < n_side; ++i) wt[i] = lut[gdeg[i]];
+            BLP_CUDA_TRY(cudaMalloc((void**)&g->node_wt[side], sizeof(unsigned) * wt.size()));
+            BLP_CUDA_TRY(cudaMemcpy(g->node_wt[side], wt.data(), sizeof(unsigned) * wt.size(),
+                                    cudaMemcpyHostToDevice));
+            g->device_bytes += (int64_t)(sizeof(unsigned) * wt.size());
+            g->row_slots[side] = true;
+            g->probe_ratio = kProbeRatio;
+            if (const char* e = getenv("BLP_PROBE_RATIO")) g->probe_ratio = std::max(1, atoi(e));
+        }
         int* d_nodes = nullptr;
         const size_t bytes = hubs.size() * (size_t)bm_bytes;
         BLP_CUDA_TRY(cudaMalloc((void**)&g->xrow[side], sizeof(unsigned long long) * (size_t)n_mid));
@@ -1019,6 +1489,24 @@ int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host
         BLP_CUDA_TRY(cudaDeviceSynchronize());
         cudaFree(d_nodes);
         g->device_bytes += (int64_t)bytes + (int64_t)sizeof(unsigned long long) * n_mid;
+    }
+    // which grouping nodes qualify for the warp-per-group kernel (BLP_LIGHT=0 turns it off)
+    const char* le = getenv("BLP_LIGHT");
+    if (!le || atoi(le) != 0) {
+        for (int side = 0; side < 2; ++side) {
+            const bool us = side == BLP_SIDE_USER;
+            const int n_side = us ? g->n_users : g->n_biz;
+            if (n_side <= 0) continue;
+            const unsigned long long* g_row = (const unsigned long long*)(us ? g->u_row : g->b_row);
+            const unsigned long long* m_row = (const unsigned long long*)(us ? g->b_row : g->u_row);
+            BLP_CUDA_TRY(cudaMalloc((void**)&g->light[side], (size_t)n_side));
+            k_flag_light<<<(n_side + 255) / 256, 256>>>(
+                n_side, g_row, us ? g->u_adj : g->b_adj,
+                g->xrow[side] ? (const unsigned long long*)g->xrow[side] : m_row, g->light[side]);
+            BLP_CUDA_TRY(cudaGetLastError());
+            g->device_bytes += n_side;
+        }
+        BLP_CUDA_TRY(cudaDeviceSynchronize());
     }
     return BLP_OK;
 }
@@ -1057,6 +1545,8 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     a.m_adjw = us ? g->b_adjw : g->u_adjw;
     a.m_xrow = g->xrow[side] ? (const unsigned long long*)g->xrow[side] : a.m_row;
     a.hub_bm = g->hub_bm[side];
+    a.node_wt = g->row_slots[side] ? g->node_wt[side] : nullptr;
+    a.probe_ratio = g->probe_ratio;
     a.n_side = us ? g->n_users : g->n_biz;
     const int n_mid = us ? g->n_biz : g->n_users;
     const int* gx = us ? pair_u : pair_b;
@@ -1098,7 +1588,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     // one stream-ordered block for all scratch of the call (an idle GPU would otherwise wait for
     // a dozen allocator calls before the first kernel): carved by a bump pointer, 256-byte aligned
     const size_t n_sz = (size_t)n, k_sz = (size_t)n_keys, i_sz = std::max(n_sz, k_sz);
-    const size_t arena_bytes = 4 * n_sz + 12 * i_sz + 8 * k_sz + 12 * n_sz + 24 * n_sz +
+    const size_t arena_bytes = 4 * n_sz + 20 * i_sz + 8 * k_sz + 12 * n_sz + 24 * n_sz +
                                (ranged ? 12 * n_sz : 0) + 64 * 256;
     unsigned char* arena = nullptr;
     size_t arena_used = 0;
@@ -1129,8 +1619,9 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     int *keys = nullptr, *scalars = nullptr, *inv = nullptr;
     int *item_key = nullptr, *item_start = nullptr, *item_end = nullptr;
     BLP_TRY_SCRATCH(alloc((void**)&keys, sizeof(int) * (size_t)n));
-    BLP_TRY_SCRATCH(alloc((void**)&scalars, sizeof(int) * 4));   // n_items, work counter, n_runs
-    BLP_TRY_SCRATCH(cudaMemsetAsync(scalars, 0, sizeof(int) * 4, st));
+    // n_items, work counter, n_runs, mode, n_light, n_heavy, light work counter
+    BLP_TRY_SCRATCH(alloc((void**)&scalars, sizeof(int) * 8));
+    BLP_TRY_SCRATCH(cudaMemsetAsync(scalars, 0, sizeof(int) * 8, st));
     if (ranged) {
         BLP_TRY_SCRATCH(alloc((void**)&a.acc_cn, sizeof(int) * (size_t)n));
         BLP_TRY_SCRATCH(alloc((void**)&a.acc_aa, sizeof(unsigned long long) * (size_t)n));
@@ -1195,13 +1686,31 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     }
     a.mode = mode;
     a.caller_y = gy;
-    BLP_TRY_SCRATCH(cudaEventRecord(g->ev[side][1], st));
-
     a.item_key = item_key;
     a.item_start = item_start;
     a.item_end = item_end;
     a.n_items = scalars;
     a.work_counter = scalars + 1;
+    // light / heavy split of the work items: light groups go to the warp-per-group kernel
+    const bool split = g->light[side] != nullptr;
+    SideArgs la{};
+    if (split) {
+        int *light_list = nullptr, *heavy_list = nullptr;
+        BLP_TRY_SCRATCH(alloc((void**)&light_list, sizeof(int) * n_items_max));
+        BLP_TRY_SCRATCH(alloc((void**)&heavy_list, sizeof(int) * n_items_max));
+        const int sblocks = (int)std::min<size_t>((n_items_max + 255) / 256, (size_t)g->sm_count * 8);
+        k_split_items<<<sblocks, 256, 0, st>>>(scalars, item_key, g->light[side], a.n_side,
+                                               light_list, heavy_list, scalars + 4);
+        BLP_TRY_SCRATCH(cudaGetLastError());
+        ++launches;
+        la = a;
+        la.item_list = light_list;
+        la.n_items = scalars + 4;
+        la.work_counter = scalars + 6;
+        a.item_list = heavy_list;
+        a.n_items = scalars + 5;
+    }
+    BLP_TRY_SCRATCH(cudaEventRecord(g->ev[side][1], st));
 
     // ---- persistent scoring grid: as many CTAs per SM as the bitmap allows
     int per_sm = 0, nt = 0, rc = BLP_OK;
@@ -1238,6 +1747,35 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
             rc = rec_mode ? launch_side<NTV, RV, true>(a, per_sm * use_sms, smem, st)  \
                           : launch_side<NTV, RV, false>(a, per_sm * use_sms, smem, st); \
     } while (0)
+    if (split) {
+        const size_t lsmem = sizeof(LightSmem) * kLightWarps;
+        if (g->light_ctas_per_sm == 0) {
+            int occ = 0;
+            cudaError_t e = cudaFuncSetAttribute(k_score_light<false>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(k_score_light<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+            if (e == cudaSuccess)
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_light<false>,
+                                                                  kLightWarps * 32, lsmem);
+            if (e != cudaSuccess || occ < 1) {
+                release();
+                set_error("blp_score_pairs: the light-group kernel does not fit on an SM");
+                return BLP_ERR_UNSUPPORTED;
+            }
+            g->light_ctas_per_sm = occ;
+        }
+        const int lgrid = g->light_ctas_per_sm * use_sms;
+        if (rec_mode) k_score_light<true><<<lgrid, kLightWarps * 32, lsmem, st>>>(la);
+        else k_score_light<false><<<lgrid, kLightWarps * 32, lsmem, st>>>(la);
+        if (cudaGetLastError() != cudaSuccess) {
+            release();
+            set_error("blp_score_pairs: launching the light-group kernel failed");
+            return BLP_ERR_CUDA;
+        }
+        ++launches;
+    }
     if (nt == 256) {
         if (ranged) BLP_DISPATCH(256, true); else BLP_DISPATCH(256, false);
     } else if (nt == 512) {
