@@ -148,7 +148,7 @@ int init_device_state(blp_graph* g, int device) {
     }
     (void)cudaGetLastError();
     for (int sd = 0; sd < 2; ++sd)
-        for (int k = 0; k < 3; ++k) BLP_CUDA_TRY(cudaEventCreate(&g->ev[sd][k]));
+        for (int k = 0; k < 4; ++k) BLP_CUDA_TRY(cudaEventCreate(&g->ev[sd][k]));
     return BLP_OK;
 }
 
@@ -334,9 +334,11 @@ extern "C" int blp_graph_destroy(blp_graph* g) {
         cudaFree(g->hub_bm[sd]);
         cudaFree(g->node_wt[sd]);
         cudaFree(g->light[sd]);
+        cudaFree(g->hubtab_cn[sd]);
+        cudaFree(g->hubtab_aa[sd]);
     }
     for (int sd = 0; sd < 2; ++sd)
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 4; ++k)
             if (g->ev[sd][k]) cudaEventDestroy(g->ev[sd][k]);
     (void)cudaGetLastError();
     delete g;
@@ -398,6 +400,8 @@ extern "C" int blp_score_stats(const blp_graph* g, int side, blp_score_stats_t* 
         BLP_CUDA_TRY(cudaEventSynchronize(g->ev[side][2]));
         BLP_CUDA_TRY(cudaEventElapsedTime(&stats->group_ms, g->ev[side][0], g->ev[side][1]));
         BLP_CUDA_TRY(cudaEventElapsedTime(&stats->score_ms, g->ev[side][1], g->ev[side][2]));
+        if (g->ev_light[side])
+            BLP_CUDA_TRY(cudaEventElapsedTime(&stats->light_ms, g->ev[side][1], g->ev[side][3]));
     }
     return BLP_OK;
 }

@@ -13,6 +13,8 @@
 #define BLP_ROW_FIRST4_BITS 28
 #define BLP_ROW_SLOT_SHIFT 52
 #define BLP_ROW_MAX_SLOTS 2047
+// expansion-side entry of a hub (xrow): 1 << 63 | table row << 35 | bitmap slot << 24 | degree
+#define BLP_XROW_ORIDX_SHIFT 35
 
 // Fixed point for the Adamic-Adar weights: integer sums are order independent.  A weight is at
 // most 1/ln 2 = 1.4427 < 2, so Q1.31 fits 32 bits; sums are kept in 64 bits.
@@ -55,8 +57,11 @@ struct blp_graph {
     // partner has a bitmap is scored by probing that bitmap with the list instead of streaming N(y).
     unsigned long long* xrow[2] = {nullptr, nullptr};   // expansion-side row descriptors (hubs tagged)
     unsigned* hub_bm[2] = {nullptr, nullptr};     // [n_hubs][bm_words]
-    unsigned char* light[2] = {nullptr, nullptr}; // per grouping node of side s: warp-per-group kernel
-    int light_ctas_per_sm = 0;
+    unsigned char* light[2] = {nullptr, nullptr}; // per grouping node of side s: 1 = warp-per-group kernel
+    int light_ctas_per_sm[2] = {};      // [rec]
+    // |N(h) & N(y)| and its weight sum, OR-hub h (row) x bitmap node y (column), per side
+    int* hubtab_cn[2] = {nullptr, nullptr};
+    unsigned long long* hubtab_aa[2] = {nullptr, nullptr};
     unsigned* node_wt[2] = {nullptr, nullptr};    // Q1.31 1/ln(deg) per grouping-side node of side s
     int hub_min_deg[2] = {0x7fffffff, 0x7fffffff};    // expansion ORs the bitmap from here on
     int probe_min_deg[2] = {0x7fffffff, 0x7fffffff};  // a bitmap exists from here on
@@ -64,7 +69,8 @@ struct blp_graph {
     int probe_ratio = 2;                              // probe when deg(y) >= ratio * |hop2(x)|
     bool row_slots[2] = {false, false};               // slot bits present in the middle rows of side s
     blp_score_stats_t stats[2] = {};
-    cudaEvent_t ev[2][3] = {};   // per side: start, after grouping, after scoring
+    cudaEvent_t ev[2][4] = {};   // per side: start, after grouping, after scoring, after the light kernel
+    bool ev_light[2] = {false, false};
     bool ev_recorded[2] = {false, false};
 };
 

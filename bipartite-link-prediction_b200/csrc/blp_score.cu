@@ -55,6 +55,11 @@ struct SideArgs {
     // probe path of the intersection: Q1.31 weight of every x-side node (null = path off)
     const unsigned* __restrict__ node_wt;
     int probe_ratio;
+    // |N(h) & N(y)| and the weight sum over it for every OR-hub h (row) and bitmap node y (column):
+    // lets the warp-per-group kernel take groups with ONE hub without touching the hub's bitmap
+    const int* __restrict__ hubtab_cn;
+    const unsigned long long* __restrict__ hubtab_aa;
+    int hubtab_stride;
     // id-range passes: when the bitmap of the whole universe does not fit (or is not wanted) in
     // shared memory the group is processed n_ranges times, pass r covering ids
     // [r*range_bits, (r+1)*range_bits); partial cn / aa wait in scratch (grouped order)
@@ -832,7 +837,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 list_len = min(row_deg(row), kProbeCap + 1);
                 if (row >> 63) {
                     const int h = atomicAdd(&ts.nhub, 1);
-                    ts.hub[h] = (int)((row >> 24) & 0x7fffffffull);
+                    ts.hub[h] = (int)((row >> 24) & (unsigned long long)BLP_ROW_MAX_SLOTS);
                     ts.cn[h] = row_deg(row);   // ts.cn is idle during the expansion
                     row = 0ull;                // degree 0: skipped by both list walkers
                     list_len = kProbeCap + 1;
@@ -1035,78 +1040,128 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
 // Measured on C2 (tools/cost_model.py): 60 % of the CTA kernel's time is per-GROUP cost -- a
 // chain of ~8 CTA barriers and ~6 dependent global round trips per group with only four groups in
 // flight per SM (four 46 KB bitmaps) -- and about half of the groups are tiny: a user with a few
-// small businesses whose expansion walks a few hundred ids.  Such a group (flagged per node at
-// graph creation: <= 32 middle nodes, none of them an OR-hub, <= kLightCap ids walked) needs no
-// bitmap over the whole universe.  Here one warp owns it: hop2(x) goes into a 4 KB open-addressing
-// hash table in shared memory (and, in insertion order, into an id list), every partner list is
-// streamed against the table, and partners that have a bitmap are scored by probing it with the
-// list.  No CTA barrier anywhere, 32 groups in flight per SM instead of 4.  The arithmetic is the
-// same integer arithmetic as in k_score_side, so the outputs are bit-identical.
+// small businesses whose expansion walks a few hundred ids.  Such a group (classified per node at
+// graph creation: <= 32 middle nodes, none of them an OR-hub, <= CAP ids walked) needs no bitmap
+// over the whole universe.  Here one warp owns it: hop2(x) goes into an open-addressing hash
+// table in shared memory (and, in insertion order, into an id list), the partner lists are
+// streamed against the table -- all lists of a 32-pair tile as ONE flattened index space, so that
+// short lists cost no pass of their own and every lane has loads in flight -- and partners that
+// have a bitmap are scored by probing it with the list.  No CTA barrier anywhere; the descriptor
+// chain of the next group is fetched in stages behind the current group's phases.  The arithmetic
+// is the same integer arithmetic as in k_score_side, so the outputs are bit-identical.
+// A group with exactly ONE hub among its middle nodes qualifies as well: hop2(x) = N(h) + S' with
+// S' = the ids of the other lists that are not in N(h); the table and the list hold S' only, a
+// streamed id that misses the table is looked up in the hub's bitmap where it lies (L2), and for a
+// partner y that has a bitmap itself |N(h) & N(y)| comes from a table precomputed at graph creation.
+// (A larger-table "medium" instance with 8 groups in flight per SM was measured and is slower than
+// the CTA kernel: one warp streaming a hub partner's list is too slow.)
 // ---------------------------------------------------------------------------------------------
-constexpr int kLightCap = 512;      // ids walked by the expansion of a light group, at most
-constexpr int kLightSlots = 1024;   // hash slots (load factor <= 0.5, typically ~0.2)
-constexpr int kLightWarps = 8;
+constexpr int kLightCap = 512, kLightSlots = 1024, kLightWarps = 8;
 constexpr int kLightEmpty = -1;
 
+template <int CAP, int SLOTS>
 struct LightSmem {
-    int table[kLightSlots];
-    int list[kLightCap];
+    int table[SLOTS];
+    int list[CAP];
+    // per pair of the tile: hits and weighted hits.  The weight sum is kept as two 32-bit words
+    // (low 24 bits / the rest) so that native 32-bit shared atomics add it exactly: a lane adds
+    // its whole share of a pair at once (<= 32 adds per pair), and a pair has < 2^24 hits.
+    unsigned aa_lo[32];
+    unsigned aa_hi[32];
+    int cn[32];
 };
 
-__device__ __forceinline__ unsigned light_hash(int id) {
-    return ((unsigned)id * 2654435761u) >> 22;   // 10 bits
+// The table is a set of 4-slot buckets (16 bytes, one 128-bit shared load).  A bucket fills from
+// slot 0 upwards, so it is full exactly when its last slot is taken; only then does a search go on
+// to the next bucket.  At the typical load (~0.2) a lookup is one load and four compares, with
+// hardly any divergence between the lanes.
+template <int SLOTS>
+__device__ __forceinline__ unsigned light_bucket(int id) {
+    static_assert((SLOTS & (SLOTS - 1)) == 0 && SLOTS >= 64, "power of two");
+    return (((unsigned)id * 2654435761u) >> 8) & (unsigned)(SLOTS / 4 - 1);
 }
-static_assert(kLightSlots == 1024, "light_hash yields 10 bits");
 
+template <int SLOTS>
 __device__ __forceinline__ bool light_has(const int* table, int id) {
-    unsigned s = light_hash(id);
+    unsigned b = light_bucket<SLOTS>(id);
     while (true) {
-        const int v = table[s];
-        if (v == id) return true;
-        if (v == kLightEmpty) return false;   // also ends the search for the padding sentinel
-        s = (s + 1) & (kLightSlots - 1);
+        const int4 v = reinterpret_cast<const int4*>(table)[b];
+        if (v.x == id || v.y == id || v.z == id || v.w == id) return true;
+        if (v.w == kLightEmpty) return false;   // bucket not full (the padding id ends here too)
+        b = (b + 1) & (SLOTS / 4 - 1);
     }
 }
 
 // true when THIS call put the id into the table
+template <int SLOTS>
 __device__ __forceinline__ bool light_insert(int* table, int id) {
-    unsigned s = light_hash(id);
+    unsigned b = light_bucket<SLOTS>(id);
     while (true) {
-        const int prev = atomicCAS(&table[s], kLightEmpty, id);
-        if (prev == kLightEmpty) return true;
-        if (prev == id) return false;
-        s = (s + 1) & (kLightSlots - 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int prev = atomicCAS(&table[4 * b + k], kLightEmpty, id);
+            if (prev == kLightEmpty) return true;
+            if (prev == id) return false;
+        }
+        b = (b + 1) & (SLOTS / 4 - 1);
     }
 }
 
 // expansion step for the four ids of one 128-bit load; new ids are appended to the list with one
 // ballot per component (list_n is warp-uniform)
-__device__ __forceinline__ void light_expand4(LightSmem& ls, int4 v, bool active, int x, int n_side,
-                                              int& list_n, int lane) {
+__device__ __forceinline__ bool hub_bit(const unsigned* hbm, int id) {
+    return (__ldg(hbm + (id >> 5)) >> (id & 31)) & 1u;
+}
+
+// hbm: bitmap of the group's single hub (null = none); ids already in it stay out of the table
+template <int SLOTS>
+__device__ __forceinline__ void light_expand4(int* table, int* list, int4 v, bool active, int x,
+                                              int n_side, const unsigned* hbm, int& list_n, int lane) {
     const int id[4] = {v.x, v.y, v.z, v.w};
+    bool want[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) want[k] = active && id[k] < n_side && id[k] != x;
+    if (hbm) {
+        bool in_hub[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) in_hub[k] = want[k] && hub_bit(hbm, id[k]);   // four loads in flight
+#pragma unroll
+        for (int k = 0; k < 4; ++k) want[k] = want[k] && !in_hub[k];
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const bool fresh = active && id[k] < n_side && id[k] != x && light_insert(ls.table, id[k]);
+        const bool fresh = want[k] && light_insert<SLOTS>(table, id[k]);
         const unsigned m = __ballot_sync(kFull, fresh);
-        if (fresh) ls.list[list_n + __popc(m & ((1u << lane) - 1u))] = id[k];
+        if (fresh) list[list_n + __popc(m & ((1u << lane) - 1u))] = id[k];
         list_n += __popc(m);
     }
 }
 
-__device__ __forceinline__ void light_test4(const int* table, int4 v, uint4 wt, unsigned& cnt,
+template <int SLOTS>
+__device__ __forceinline__ void light_test4(const int* table, int4 v, uint4 wt, int x,
+                                            const unsigned* hbm, unsigned& cnt,
                                             unsigned long long& acc) {
     const int id[4] = {v.x, v.y, v.z, v.w};
     const unsigned w[4] = {wt.x, wt.y, wt.z, wt.w};
+    bool hit[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hit[k] = light_has<SLOTS>(table, id[k]);
+    if (hbm) {   // hop2(x) also holds N(h) \ {x}; bit n_side (the padding id) is never on
+        bool in_hub[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) in_hub[k] = !hit[k] && id[k] != x && hub_bit(hbm, id[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hit[k] = hit[k] || in_hub[k];
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if (light_has(table, id[k])) {
+        if (hit[k]) {
             ++cnt;
             acc += w[k];
         }
 }
 
-// exact warp sum of per-lane weight sums < 2^40 (three REDUX over 16-bit limbs would be needed
-// beyond that: a lane adds at most deg/32 + 4 weights of < 2^31)
+// exact warp sum of per-lane weight sums (three 16/16/32-bit limbs, REDUX each)
 __device__ __forceinline__ unsigned long long light_sum64(unsigned long long acc) {
     const unsigned l0 = __reduce_add_sync(kFull, (unsigned)(acc & 0xffffull));
     const unsigned l1 = __reduce_add_sync(kFull, (unsigned)((acc >> 16) & 0xffffull));
@@ -1114,109 +1169,164 @@ __device__ __forceinline__ unsigned long long light_sum64(unsigned long long acc
     return ((unsigned long long)l2 << 32) + ((unsigned long long)l1 << 16) + l0;
 }
 
-template <bool REC>
-__global__ void __launch_bounds__(kLightWarps * 32) k_score_light(SideArgs a) {
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(kFull, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// Flattened lists: lane l holds the inclusive prefix of the lengths.  Which lane's list owns the
+// flat index i (< total)?  = number of lanes whose inclusive prefix is <= i.
+__device__ __forceinline__ int seg_search(int incl, int i) {
+    int lo = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const int t = __shfl_sync(kFull, incl, lo + s - 1);
+        if (t <= i) lo += s;
+    }
+    return lo;
+}
+
+// descriptor chain of one group, fetched in stages (every field warp-uniform except m / mrow)
+struct LightRegs {
+    int it;                     // item index, -1 = none
+    int x;
+    int p0, p1;
+    unsigned long long xrow;
+    int m;                      // lane < deg(x): this lane's middle node
+    unsigned long long mrow;    // ... and its row
+};
+__device__ __forceinline__ void light_stage_a(const SideArgs& a, LightRegs& g, int c, int n_items) {
+    g.it = c < n_items ? a.item_list[c] : -1;
+}
+__device__ __forceinline__ void light_stage_b(const SideArgs& a, LightRegs& g) {
+    g.x = 0;
+    g.p0 = g.p1 = 0;
+    if (g.it >= 0) {
+        g.x = a.item_key[g.it];
+        g.p0 = a.item_start[g.it];
+        g.p1 = a.item_end[g.it];
+    }
+}
+__device__ __forceinline__ void light_stage_c(const SideArgs& a, LightRegs& g) {
+    g.xrow = g.it >= 0 ? a.g_row[g.x] : 0ull;
+}
+__device__ __forceinline__ void light_stage_d(const SideArgs& a, LightRegs& g, int lane) {
+    g.m = lane < row_deg(g.xrow) ? a.g_adj[row_first4(g.xrow) * 4 + lane] : -1;
+}
+__device__ __forceinline__ void light_stage_e(const SideArgs& a, LightRegs& g) {
+    g.mrow = g.m >= 0 ? a.m_xrow[g.m] : 0ull;   // a hub's entry carries flag, slot and table row
+}
+
+template <int CAP, int SLOTS, int WARPS, bool REC>
+__global__ void __launch_bounds__(WARPS * 32, 2048 / (WARPS * 32) / 2) k_score_light(SideArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef LightSmem<CAP, SLOTS> Smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    LightSmem& ls = reinterpret_cast<LightSmem*>(smem_raw)[warp];
+    Smem& ls = reinterpret_cast<Smem*>(smem_raw)[warp];
     const int n_items = *a.n_items;
     if (*a.mode == MODE_RUNS) a.pg = nullptr;
     const int4* adj4 = reinterpret_cast<const int4*>(a.m_adj);
     const uint4* adjw4 = reinterpret_cast<const uint4*>(a.m_adjw);
+    const int4 sent4 = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
+    const int4 empty4 = make_int4(kLightEmpty, kLightEmpty, kLightEmpty, kLightEmpty);
     {
         int4* t4 = reinterpret_cast<int4*>(ls.table);
-        for (int i = lane; i < kLightSlots / 4; i += 32)
-            t4[i] = make_int4(kLightEmpty, kLightEmpty, kLightEmpty, kLightEmpty);
+        for (int i = lane; i < SLOTS / 4; i += 32) t4[i] = empty4;
     }
     __syncwarp();
-    int c = 0;
-    if (lane == 0) c = atomicAdd(a.work_counter, 1);
+    // two claims ahead: the index of the next group is known when the current one starts
+    int c = 0, c1 = 0;
+    if (lane == 0) {
+        c = atomicAdd(a.work_counter, 1);
+        c1 = atomicAdd(a.work_counter, 1);
+    }
     c = __shfl_sync(kFull, c, 0);
+    c1 = __shfl_sync(kFull, c1, 0);
+    LightRegs cur;
+    light_stage_a(a, cur, c, n_items);
+    light_stage_b(a, cur);
+    light_stage_c(a, cur);
+    light_stage_d(a, cur, lane);
+    light_stage_e(a, cur);
     while (c < n_items) {
-        int c_next = 0;
-        if (lane == 0) c_next = atomicAdd(a.work_counter, 1);   // latency hides behind this group
-        const int it = a.item_list[c];
-        const int x = a.item_key[it];
-        const long long p0 = a.item_start[it], p1 = a.item_end[it];
-        const unsigned long long xrow = a.g_row[x];
-        const int xdeg = row_deg(xrow);   // 1..32 by the light flag
-        // ---- expansion: every list N(m), m in N(x), into the table and the list
-        unsigned long long mrow = 0ull;
-        if (lane < xdeg) mrow = a.m_row[a.g_adj[row_first4(xrow) * 4 + lane]];
-        const int mn4 = (row_deg(mrow) + 3) >> 2;
+        int c2 = 0;
+        if (lane == 0) c2 = atomicAdd(a.work_counter, 1);
+        LightRegs nxt;
+        light_stage_a(a, nxt, c1, n_items);
+        const int x = cur.x;
+        const long long p0 = cur.p0, p1 = cur.p1;
+        const int xdeg = row_deg(cur.xrow);   // 1..32 by the class flag
+        // partners of the first pair tile: issued now, their rows after the expansion
+        int2 iy0 = make_int2(0, 0);
+        if (p0 + lane < p1) iy0 = pair_at(a, p0 + lane);
+        // the group's hub, if it has one (at most one, by its class)
+        const unsigned hub_lanes = __ballot_sync(kFull, (cur.mrow >> 63) != 0);
+        const unsigned* hbm = nullptr;
+        int hub_deg = 0, hub_tab = 0;
+        if (hub_lanes) {
+            const unsigned long long hr = __shfl_sync(kFull, cur.mrow, __ffs(hub_lanes) - 1);
+            hbm = a.hub_bm + (size_t)((hr >> 24) & (unsigned long long)BLP_ROW_MAX_SLOTS) * (size_t)a.hub_words;
+            hub_deg = row_deg(hr);
+            hub_tab = (int)((hr >> BLP_XROW_ORIDX_SHIFT) & (unsigned long long)BLP_ROW_MAX_SLOTS) *
+                      a.hubtab_stride;
+        }
+        // ---- expansion: the lists N(m), m in N(x), as one flattened space of 128-bit loads
         int list_n = 0;
         {
-            const int sub = lane & 3, slot = lane >> 2;
-            for (int base = 0; base < xdeg; base += 8) {
-                const unsigned long long r = __shfl_sync(kFull, mrow, min(base + slot, 31));
-                const int n4 = base + slot < xdeg ? (row_deg(r) + 3) >> 2 : 0;
-                const bool mine = n4 > 0 && n4 <= kShortV4 && sub < n4;
-                if (!__any_sync(kFull, mine)) continue;
-                int4 v = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
-                if (mine) v = ldg_stream(adj4 + row_first4(r) + sub);
-                light_expand4(ls, v, mine, x, a.n_side, list_n, lane);
-            }
-            unsigned longs = __ballot_sync(kFull, mn4 > kShortV4);
-            while (longs) {
-                const int j = __ffs(longs) - 1;
-                longs &= longs - 1;
-                const unsigned long long r = __shfl_sync(kFull, mrow, j);
-                const int n4 = (row_deg(r) + 3) >> 2;
-                const long long at = row_first4(r);
-                for (int i0 = 0; i0 < n4; i0 += 32) {
-                    const bool mine = i0 + lane < n4;
-                    int4 v = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
-                    if (mine) v = ldg_stream(adj4 + at + i0 + lane);
-                    light_expand4(ls, v, mine, x, a.n_side, list_n, lane);
+            const int mn4 = (cur.mrow >> 63) ? 0 : (row_deg(cur.mrow) + 3) >> 2;
+            const long long mat = row_first4(cur.mrow);
+            const int incl = warp_incl_scan(mn4, lane);
+            const int excl = incl - mn4;
+            const int total = __shfl_sync(kFull, incl, 31);
+            for (int i0 = 0; i0 < total; i0 += 64) {
+                int4 v[2];
+                bool ok[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = i0 + 32 * h + lane;
+                    ok[h] = i < total;
+                    const int ii = ok[h] ? i : total - 1;
+                    const int j = seg_search(incl, ii);
+                    const int off = ii - __shfl_sync(kFull, excl, j);
+                    const long long at = __shfl_sync(kFull, mat, j) + off;
+                    v[h] = ok[h] ? ldg_stream(adj4 + at) : sent4;
                 }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (i0 + 32 * h < total)
+                        light_expand4<SLOTS>(ls.table, ls.list, v[h], ok[h], x, a.n_side, hbm, list_n,
+                                             lane);
             }
         }
         __syncwarp();
-        const int hop2 = list_n;   // x itself was never inserted
+        // x itself was never inserted; it is in N(h), and so is nothing else of the list
+        const int hop2 = list_n + (hbm ? hub_deg - 1 : 0);
+        light_stage_b(a, nxt);
         // ---- the pairs of the group, 32 at a time: lane l owns pair tb + l
         for (long long tb = p0; tb < p1; tb += 32) {
             const int count = (int)min(32ll, p1 - tb);
             unsigned long long row = 0ull;
-            int idx = 0;
+            int idx = 0, py = -1;
             if (lane < count) {
-                const int2 iy = pair_at(a, tb + lane);
+                const int2 iy = tb == p0 ? iy0 : pair_at(a, tb + lane);
                 row = a.m_row[iy.y];
                 idx = iy.x;
+                py = iy.y;
             }
+            if (tb == p0) light_stage_c(a, nxt);
             const int pdeg = row_deg(row);
-            const int pn4 = (pdeg + 3) >> 2;
             const bool by_probe = lane < count && a.node_wt != nullptr && row_slot1(row) > 0 &&
-                                  (long long)a.probe_ratio * hop2 <= pdeg;
+                                  (long long)a.probe_ratio * list_n <= pdeg;
+            ls.cn[lane] = 0;
+            ls.aa_lo[lane] = 0u;
+            ls.aa_hi[lane] = 0u;
+            __syncwarp();
             unsigned my_cn = 0;
             unsigned long long my_aa = 0ull;
-            // short partner lists: 4 lanes per list, 8 lists per pass
-            {
-                const int sub = lane & 3, slot = lane >> 2;
-                for (int base = 0; base < count; base += 8) {
-                    const unsigned long long r = __shfl_sync(kFull, row, min(base + slot, 31));
-                    const int n4 = base + slot < count ? (row_deg(r) + 3) >> 2 : 0;
-                    const bool mine = n4 > 0 && n4 <= kShortV4 && sub < n4;
-                    if (!__any_sync(kFull, mine)) continue;
-                    unsigned cnt = 0;
-                    unsigned long long acc = 0ull;
-                    if (mine && hop2 > 0) {
-                        const long long at = row_first4(r) + sub;
-                        light_test4(ls.table, ldg_stream(adj4 + at), ldg_stream_u(adjw4 + at), cnt, acc);
-                    }
-                    cnt += __shfl_xor_sync(kFull, cnt, 1);
-                    cnt += __shfl_xor_sync(kFull, cnt, 2);
-                    acc += __shfl_xor_sync(kFull, acc, 1);
-                    acc += __shfl_xor_sync(kFull, acc, 2);
-                    // the result of list base + s sits in lanes 4s..4s+3; its owner is lane base + s
-                    const int src = ((lane - base) & 7) * 4;
-                    const unsigned got_c = __shfl_sync(kFull, cnt, src);
-                    const unsigned long long got_a = __shfl_sync(kFull, acc, src);
-                    if (lane >= base && lane < base + 8 && pn4 > 0 && pn4 <= kShortV4) {
-                        my_cn = got_c;
-                        my_aa = got_a;
-                    }
-                }
-            }
             // partners with a bitmap: the hop-2 list against the bitmap
             unsigned todo = __ballot_sync(kFull, by_probe);
             while (todo) {
@@ -1226,12 +1336,26 @@ __global__ void __launch_bounds__(kLightWarps * 32) k_score_light(SideArgs a) {
                 const unsigned* hb = a.hub_bm + (size_t)(row_slot1(r) - 1) * (size_t)a.hub_words;
                 unsigned cnt = 0;
                 unsigned long long acc = 0ull;
-                for (int i0 = lane; i0 < hop2; i0 += 128) {
+                if (hbm && lane == 0) {
+                    // the hub's share |N(h) & N(y)| from the table, minus x when x is in N(y)
+                    const int t = hub_tab + row_slot1(r) - 1;
+                    cnt = (unsigned)a.hubtab_cn[t];
+                    acc = a.hubtab_aa[t];
+                }
+                if (hbm) {
+                    const int yj = __shfl_sync(kFull, py, j);
+                    const bool x_in = __any_sync(kFull, cur.m == yj);   // y in N(x)
+                    if (x_in && lane == 0) {
+                        cnt -= 1u;
+                        acc -= (unsigned long long)__ldg(a.node_wt + x);
+                    }
+                }
+                for (int i0 = lane; i0 < list_n; i0 += 128) {
                     int w[4];
                     unsigned word[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k)   // bit n_side is never on in a hub bitmap
-                        w[k] = i0 + 32 * k < hop2 ? ls.list[i0 + 32 * k] : a.n_side;
+                        w[k] = i0 + 32 * k < list_n ? ls.list[i0 + 32 * k] : a.n_side;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) word[k] = __ldg(hb + (w[k] >> 5));
 #pragma unroll
@@ -1248,38 +1372,63 @@ __global__ void __launch_bounds__(kLightWarps * 32) k_score_light(SideArgs a) {
                     my_aa = cnt > 0 ? acc : 0ull;
                 }
             }
-            // every other partner list: streamed by the whole warp against the table
-            todo = __ballot_sync(kFull, lane < count && pn4 > kShortV4 && !by_probe);
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const unsigned long long r = __shfl_sync(kFull, row, j);
-                const int n4 = (row_deg(r) + 3) >> 2;
-                const long long at = row_first4(r);
-                unsigned cnt = 0;
-                unsigned long long acc = 0ull;
-                if (hop2 > 0) {
-                    for (int i0 = lane; i0 < n4; i0 += 64) {
-                        const bool second = i0 + 32 < n4;
-                        const int4 v0 = ldg_stream(adj4 + at + i0);
-                        const uint4 w0 = ldg_stream_u(adjw4 + at + i0);
-                        int4 v1 = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
-                        uint4 w1 = make_uint4(0u, 0u, 0u, 0u);
-                        if (second) {
-                            v1 = ldg_stream(adj4 + at + i0 + 32);
-                            w1 = ldg_stream_u(adjw4 + at + i0 + 32);
+            // every other partner list, flattened: streamed against the table (and the hub's bitmap)
+            if (hop2 > 0) {
+                const int pn4 = (lane < count && !by_probe) ? (pdeg + 3) >> 2 : 0;
+                const long long pat = row_first4(row);
+                const int incl = warp_incl_scan(pn4, lane);
+                const int excl = incl - pn4;
+                const int total = __shfl_sync(kFull, incl, 31);
+                int run_own = 0;
+                unsigned run_cnt = 0;
+                unsigned long long run_acc = 0ull;
+                for (int i0 = 0; i0 < total; i0 += 64) {
+                    int4 v[2];
+                    uint4 wt[2];
+                    int own[2];
+                    bool ok[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int i = i0 + 32 * h + lane;
+                        ok[h] = i < total;
+                        const int ii = ok[h] ? i : total - 1;
+                        own[h] = seg_search(incl, ii);
+                        const int off = ii - __shfl_sync(kFull, excl, own[h]);
+                        const long long at = __shfl_sync(kFull, pat, own[h]) + off;
+                        v[h] = ok[h] ? ldg_stream(adj4 + at) : sent4;
+                        wt[h] = ok[h] ? ldg_stream_u(adjw4 + at) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (ok[h]) {
+                            // a lane meets the 128-bit words of one pair back to back: it keeps
+                            // their sum in registers and adds it to the pair's totals once
+                            if (own[h] != run_own) {
+                                if (run_cnt > 0) {
+                                    atomicAdd(&ls.cn[run_own], (int)run_cnt);
+                                    atomicAdd(&ls.aa_lo[run_own], (unsigned)(run_acc & 0xffffffull));
+                                    atomicAdd(&ls.aa_hi[run_own], (unsigned)(run_acc >> 24));
+                                }
+                                run_own = own[h];
+                                run_cnt = 0;
+                                run_acc = 0ull;
+                            }
+                            light_test4<SLOTS>(ls.table, v[h], wt[h], x, hbm, run_cnt, run_acc);
                         }
-                        light_test4(ls.table, v0, w0, cnt, acc);
-                        if (second) light_test4(ls.table, v1, w1, cnt, acc);
                     }
                 }
-                cnt = __reduce_add_sync(kFull, cnt);
-                if (cnt > 0) acc = light_sum64(acc);
-                if (lane == j) {
-                    my_cn = cnt;
-                    my_aa = cnt > 0 ? acc : 0ull;
+                if (run_cnt > 0) {
+                    atomicAdd(&ls.cn[run_own], (int)run_cnt);
+                    atomicAdd(&ls.aa_lo[run_own], (unsigned)(run_acc & 0xffffffull));
+                    atomicAdd(&ls.aa_hi[run_own], (unsigned)(run_acc >> 24));
+                }
+                __syncwarp();
+                if (!by_probe) {
+                    my_cn = (unsigned)ls.cn[lane];
+                    my_aa = ((unsigned long long)ls.aa_hi[lane] << 24) + ls.aa_lo[lane];
                 }
             }
+            if (tb == p0) light_stage_d(a, nxt, lane);
             // epilogue: same expressions as k_score_side
             if (lane < count) {
                 const int cnn = (int)my_cn;
@@ -1300,23 +1449,31 @@ __global__ void __launch_bounds__(kLightWarps * 32) k_score_light(SideArgs a) {
                 if (a.pa) a.pa[idx] = (long long)xdeg * (long long)pdeg;
                 if (a.hop2) a.hop2[idx] = hop2;
             }
+            __syncwarp();
+        }
+        if (p0 >= p1) {   // (never: an item has at least one pair)
+            light_stage_c(a, nxt);
+            light_stage_d(a, nxt, lane);
         }
         // leave the table empty for the next group
-        __syncwarp();
-        if (hop2 > 0) {
+        if (list_n > 0) {
             int4* t4 = reinterpret_cast<int4*>(ls.table);
-            for (int i = lane; i < kLightSlots / 4; i += 32)
-                t4[i] = make_int4(kLightEmpty, kLightEmpty, kLightEmpty, kLightEmpty);
+            for (int i = lane; i < SLOTS / 4; i += 32) t4[i] = empty4;
         }
         __syncwarp();
-        c = __shfl_sync(kFull, c_next, 0);
+        light_stage_e(a, nxt);
+        cur = nxt;
+        c = c1;
+        c1 = __shfl_sync(kFull, c2, 0);
     }
 }
 
 // Per node of the grouping side: can its group go to k_score_light?  (run once per graph)
+// Yes when it has <= 32 middle nodes, at most one of them an OR-hub (and only if the hub tables
+// exist), and the other lists together hold <= kLightCap ids.
 __global__ void k_flag_light(int n_side, const unsigned long long* __restrict__ g_row,
                              const int* __restrict__ g_adj,
-                             const unsigned long long* __restrict__ m_xrow,
+                             const unsigned long long* __restrict__ m_xrow, int max_hubs,
                              unsigned char* __restrict__ light) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n_side) return;
@@ -1324,44 +1481,108 @@ __global__ void k_flag_light(int n_side, const unsigned long long* __restrict__ 
     const int d = row_deg(xr);
     bool ok = d >= 1 && d <= 32;
     long long walked = 0;
+    int hubs = 0;
     if (ok) {
         const int* adj = g_adj + row_first4(xr) * 4;
         for (int i = 0; i < d; ++i) {
             const unsigned long long r = m_xrow[adj[i]];
-            if (r >> 63) ok = false;   // the expansion ORs a hub bitmap for this one
-            walked += row_deg(r);
+            if (r >> 63) ++hubs;
+            else walked += row_deg(r);
         }
     }
-    light[x] = (ok && walked <= kLightCap) ? 1 : 0;
+    light[x] = (ok && hubs <= max_hubs && walked <= kLightCap) ? 1 : 0;
 }
 
-// Items -> two lists of item indices (light groups / everything else), order irrelevant.
-__global__ void k_split_items(const int* __restrict__ n_items, const int* __restrict__ item_key,
+// One CTA per (bitmap node y, OR-hub h): |N(h) & N(y)| and the Q1.31 weight sum over it.
+__global__ void k_hub_tables(const int* __restrict__ or_nodes, int n_bm,
+                             const unsigned long long* __restrict__ m_row,
+                             const int* __restrict__ m_adj, const unsigned* __restrict__ hub_bm,
+                             int bm_words, const unsigned* __restrict__ node_wt,
+                             int* __restrict__ tab_cn, unsigned long long* __restrict__ tab_aa) {
+    const int y = blockIdx.x, o = blockIdx.y;
+    const unsigned long long row = m_row[or_nodes[o]];
+    const int* adj = m_adj + row_first4(row) * 4;
+    const unsigned* bm = hub_bm + (size_t)y * bm_words;
+    const int padded = ((row_deg(row) + 3) >> 2) << 2;   // rows are bank-striped: padding is interleaved
+    unsigned cnt = 0;
+    unsigned long long acc = 0ull;
+    for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+        const int id = adj[i];   // the padding id's bit is never on
+        if ((bm[id >> 5] >> (id & 31)) & 1u) {
+            ++cnt;
+            acc += node_wt[id];
+        }
+    }
+    __shared__ unsigned s_cnt;
+    __shared__ unsigned long long s_acc;
+    if (threadIdx.x == 0) {
+        s_cnt = 0;
+        s_acc = 0ull;
+    }
+    __syncthreads();
+    cnt = __reduce_add_sync(kFull, cnt);
+    if (cnt > 0) {
+        acc = light_sum64(acc);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_cnt, cnt);
+            atomicAdd(&s_acc, acc);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tab_cn[(size_t)o * n_bm + y] = (int)s_cnt;
+        tab_aa[(size_t)o * n_bm + y] = s_acc;
+    }
+}
+
+// Items -> two lists of item indices (warp-per-group kernel / CTA kernel), any order.
+enum { SC_N_ITEMS = 0, SC_HEAVY_WORK = 1, SC_N_RUNS = 2, SC_MODE = 3, SC_N_LIGHT = 4, SC_N_HEAVY = 5,
+       SC_LIGHT_WORK = 6, SC_COUNT = 8 };
+__global__ void k_split_items(int* __restrict__ scalars, const int* __restrict__ item_key,
                               const unsigned char* __restrict__ light, int n_side,
-                              int* __restrict__ light_list, int* __restrict__ heavy_list,
-                              int* __restrict__ counts /* [0] light, [1] heavy */) {
-    const int n = *n_items;
+                              int* __restrict__ light_list, int* __restrict__ heavy_list) {
+    const int n = scalars[SC_N_ITEMS];
     const int lane = threadIdx.x & 31;
     const int stride = gridDim.x * blockDim.x;
     for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += stride) {
         const int i = base + lane;
-        int cls = -1;
+        int cls = -1;   // 0 CTA kernel, 1 warp-per-group kernel
         if (i < n) {
             const int key = item_key[i];
-            cls = (key < n_side && light[key]) ? 0 : 1;
+            cls = key < n_side ? light[key] : 0;
         }
-        const unsigned ml = __ballot_sync(kFull, cls == 0), mh = __ballot_sync(kFull, cls == 1);
-        int bl = 0, bh = 0;
-        if (lane == 0) {
-            if (ml) bl = atomicAdd(&counts[0], __popc(ml));
-            if (mh) bh = atomicAdd(&counts[1], __popc(mh));
-        }
-        bl = __shfl_sync(kFull, bl, 0);
-        bh = __shfl_sync(kFull, bh, 0);
         const unsigned lt = (1u << lane) - 1u;
-        if (cls == 0) light_list[bl + __popc(ml & lt)] = i;
-        if (cls == 1) heavy_list[bh + __popc(mh & lt)] = i;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const unsigned m = __ballot_sync(kFull, cls == k);
+            int b = 0;
+            if (lane == 0 && m) b = atomicAdd(&scalars[k == 0 ? SC_N_HEAVY : SC_N_LIGHT], __popc(m));
+            b = __shfl_sync(kFull, b, 0);
+            int* dst = k == 0 ? heavy_list : light_list;
+            if (cls == k) dst[b + __popc(m & lt)] = i;
+        }
     }
+}
+
+template <int CAP, int SLOTS, int WARPS, bool REC>
+static int launch_light(blp_graph* g, const SideArgs& a, int use_sms, cudaStream_t st) {
+    const size_t smem = sizeof(LightSmem<CAP, SLOTS>) * WARPS;
+    int& per_sm = g->light_ctas_per_sm[REC ? 1 : 0];
+    if (per_sm == 0) {
+        BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_light<CAP, SLOTS, WARPS, REC>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        BLP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, k_score_light<CAP, SLOTS, WARPS, REC>, WARPS * 32, smem));
+        if (occ < 1) {
+            set_error("blp_score_pairs: the warp-per-group kernel does not fit on an SM");
+            return BLP_ERR_UNSUPPORTED;
+        }
+        per_sm = occ;
+    }
+    k_score_light<CAP, SLOTS, WARPS, REC><<<per_sm * use_sms, WARPS * 32, smem, st>>>(a);
+    BLP_CUDA_TRY(cudaGetLastError());
+    return BLP_OK;
 }
 
 template <int NT, bool RANGED, bool REC>
@@ -1448,10 +1669,15 @@ int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host
         // the middle rows themselves learn which of them has a bitmap (read by the intersection)
         std::vector<unsigned long long> mrow;
         if (probing) mrow = xrow;
+        std::vector<int> or_nodes;   // the hubs the expansion ORs, in table-row order
         for (size_t h = 0; h < hubs.size(); ++h) {
             if (probing) mrow[hubs[h]] |= (unsigned long long)(h + 1) << BLP_ROW_SLOT_SHIFT;
-            if (min_deg > 0 && mdeg[hubs[h]] >= min_deg)   // the expansion ORs this one
-                xrow[hubs[h]] = (1ull << 63) | ((unsigned long long)h << 24) | (unsigned)mdeg[hubs[h]];
+            if (min_deg > 0 && mdeg[hubs[h]] >= min_deg) {   // the expansion ORs this one
+                xrow[hubs[h]] = (1ull << 63) |
+                                ((unsigned long long)or_nodes.size() << BLP_XROW_ORIDX_SHIFT) |
+                                ((unsigned long long)h << 24) | (unsigned)mdeg[hubs[h]];
+                or_nodes.push_back(hubs[h]);
+            }
         }
         if (probing) {
             BLP_CUDA_TRY(cudaMemcpy(const_cast<unsigned long long*>(d_mrow), mrow.data(),
@@ -1489,6 +1715,26 @@ int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host
         BLP_CUDA_TRY(cudaDeviceSynchronize());
         cudaFree(d_nodes);
         g->device_bytes += (int64_t)bytes + (int64_t)sizeof(unsigned long long) * n_mid;
+        // hub x bitmap-node intersection tables (for one-hub groups in the warp-per-group kernel);
+        // skipped when they would take more than ~2e9 probes to fill
+        long long or_ids = 0;
+        for (int m : or_nodes) or_ids += mdeg[m];
+        if (probing && !or_nodes.empty() && or_ids * (long long)hubs.size() <= 2000000000LL) {
+            const size_t cells = or_nodes.size() * hubs.size();
+            int* d_or = nullptr;
+            BLP_CUDA_TRY(cudaMalloc((void**)&d_or, sizeof(int) * or_nodes.size()));
+            BLP_CUDA_TRY(cudaMemcpy(d_or, or_nodes.data(), sizeof(int) * or_nodes.size(),
+                                    cudaMemcpyHostToDevice));
+            BLP_CUDA_TRY(cudaMalloc((void**)&g->hubtab_cn[side], sizeof(int) * cells));
+            BLP_CUDA_TRY(cudaMalloc((void**)&g->hubtab_aa[side], sizeof(unsigned long long) * cells));
+            k_hub_tables<<<dim3((unsigned)hubs.size(), (unsigned)or_nodes.size()), 256>>>(
+                d_or, (int)hubs.size(), d_mrow, us ? g->b_adj : g->u_adj, g->hub_bm[side], words,
+                g->node_wt[side], g->hubtab_cn[side], g->hubtab_aa[side]);
+            BLP_CUDA_TRY(cudaGetLastError());
+            BLP_CUDA_TRY(cudaDeviceSynchronize());
+            cudaFree(d_or);
+            g->device_bytes += (int64_t)(cells * 12);
+        }
     }
     // which grouping nodes qualify for the warp-per-group kernel (BLP_LIGHT=0 turns it off)
     const char* le = getenv("BLP_LIGHT");
@@ -1500,9 +1746,12 @@ int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host
             const unsigned long long* g_row = (const unsigned long long*)(us ? g->u_row : g->b_row);
             const unsigned long long* m_row = (const unsigned long long*)(us ? g->b_row : g->u_row);
             BLP_CUDA_TRY(cudaMalloc((void**)&g->light[side], (size_t)n_side));
+            const char* he = getenv("BLP_LIGHT_HUBS");   // BLP_LIGHT_HUBS=0: hub-free groups only
+            const int max_hubs = (g->hubtab_cn[side] && !(he && atoi(he) == 0)) ? 1 : 0;
             k_flag_light<<<(n_side + 255) / 256, 256>>>(
                 n_side, g_row, us ? g->u_adj : g->b_adj,
-                g->xrow[side] ? (const unsigned long long*)g->xrow[side] : m_row, g->light[side]);
+                g->xrow[side] ? (const unsigned long long*)g->xrow[side] : m_row, max_hubs,
+                g->light[side]);
             BLP_CUDA_TRY(cudaGetLastError());
             g->device_bytes += n_side;
         }
@@ -1532,6 +1781,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     stats = blp_score_stats_t{};
     stats.n_pairs = n;
     g->ev_recorded[side] = false;
+    g->ev_light[side] = false;
     if (n == 0) return BLP_OK;
 
     const bool us = side == BLP_SIDE_USER;
@@ -1547,6 +1797,9 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     a.hub_bm = g->hub_bm[side];
     a.node_wt = g->row_slots[side] ? g->node_wt[side] : nullptr;
     a.probe_ratio = g->probe_ratio;
+    a.hubtab_cn = g->hubtab_cn[side];
+    a.hubtab_aa = g->hubtab_aa[side];
+    a.hubtab_stride = g->n_hubs[side];
     a.n_side = us ? g->n_users : g->n_biz;
     const int n_mid = us ? g->n_biz : g->n_users;
     const int* gx = us ? pair_u : pair_b;
@@ -1619,9 +1872,9 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     int *keys = nullptr, *scalars = nullptr, *inv = nullptr;
     int *item_key = nullptr, *item_start = nullptr, *item_end = nullptr;
     BLP_TRY_SCRATCH(alloc((void**)&keys, sizeof(int) * (size_t)n));
-    // n_items, work counter, n_runs, mode, n_light, n_heavy, light work counter
-    BLP_TRY_SCRATCH(alloc((void**)&scalars, sizeof(int) * 8));
-    BLP_TRY_SCRATCH(cudaMemsetAsync(scalars, 0, sizeof(int) * 8, st));
+    // device-side scalars of the call, see the SC_* indices
+    BLP_TRY_SCRATCH(alloc((void**)&scalars, sizeof(int) * SC_COUNT));
+    BLP_TRY_SCRATCH(cudaMemsetAsync(scalars, 0, sizeof(int) * SC_COUNT, st));
     if (ranged) {
         BLP_TRY_SCRATCH(alloc((void**)&a.acc_cn, sizeof(int) * (size_t)n));
         BLP_TRY_SCRATCH(alloc((void**)&a.acc_aa, sizeof(unsigned long long) * (size_t)n));
@@ -1700,15 +1953,15 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         BLP_TRY_SCRATCH(alloc((void**)&heavy_list, sizeof(int) * n_items_max));
         const int sblocks = (int)std::min<size_t>((n_items_max + 255) / 256, (size_t)g->sm_count * 8);
         k_split_items<<<sblocks, 256, 0, st>>>(scalars, item_key, g->light[side], a.n_side,
-                                               light_list, heavy_list, scalars + 4);
+                                               light_list, heavy_list);
         BLP_TRY_SCRATCH(cudaGetLastError());
         ++launches;
         la = a;
         la.item_list = light_list;
-        la.n_items = scalars + 4;
-        la.work_counter = scalars + 6;
+        la.n_items = scalars + SC_N_LIGHT;
+        la.work_counter = scalars + SC_LIGHT_WORK;
         a.item_list = heavy_list;
-        a.n_items = scalars + 5;
+        a.n_items = scalars + SC_N_HEAVY;
     }
     BLP_TRY_SCRATCH(cudaEventRecord(g->ev[side][1], st));
 
@@ -1748,33 +2001,16 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
                           : launch_side<NTV, RV, false>(a, per_sm * use_sms, smem, st); \
     } while (0)
     if (split) {
-        const size_t lsmem = sizeof(LightSmem) * kLightWarps;
-        if (g->light_ctas_per_sm == 0) {
-            int occ = 0;
-            cudaError_t e = cudaFuncSetAttribute(k_score_light<false>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(k_score_light<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
-            if (e == cudaSuccess)
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_score_light<false>,
-                                                                  kLightWarps * 32, lsmem);
-            if (e != cudaSuccess || occ < 1) {
-                release();
-                set_error("blp_score_pairs: the light-group kernel does not fit on an SM");
-                return BLP_ERR_UNSUPPORTED;
-            }
-            g->light_ctas_per_sm = occ;
-        }
-        const int lgrid = g->light_ctas_per_sm * use_sms;
-        if (rec_mode) k_score_light<true><<<lgrid, kLightWarps * 32, lsmem, st>>>(la);
-        else k_score_light<false><<<lgrid, kLightWarps * 32, lsmem, st>>>(la);
-        if (cudaGetLastError() != cudaSuccess) {
+        // the warp-per-group kernel first (32 groups in flight per SM)
+        const int lrc =
+            rec_mode ? launch_light<kLightCap, kLightSlots, kLightWarps, true>(g, la, use_sms, st)
+                     : launch_light<kLightCap, kLightSlots, kLightWarps, false>(g, la, use_sms, st);
+        if (lrc != BLP_OK) {
             release();
-            set_error("blp_score_pairs: launching the light-group kernel failed");
-            return BLP_ERR_CUDA;
+            return lrc;
         }
         ++launches;
+        g->ev_light[side] = cudaEventRecord(g->ev[side][3], st) == cudaSuccess;
     }
     if (nt == 256) {
         if (ranged) BLP_DISPATCH(256, true); else BLP_DISPATCH(256, false);

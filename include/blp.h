@@ -75,7 +75,8 @@ typedef struct blp_score_stats_t {
     int32_t smem_bytes;       /* dynamic shared memory per CTA */
     int32_t range_passes;     /* id-range passes over the hop-2 bitmap (1 = fits shared memory) */
     float group_ms;           /* CUDA-event time of the grouping kernels (count, scan, scatter) */
-    float score_ms;           /* CUDA-event time of the scoring kernel alone, on its own stream */
+    float score_ms;           /* CUDA-event time of the scoring kernels alone, on their own stream */
+    float light_ms;           /* ... of which the warp-per-group kernel (light groups), 0 if not used */
 } blp_score_stats_t;
 
 int blp_version(void);

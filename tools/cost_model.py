@@ -22,12 +22,12 @@ dv = np.where(pv >= 0, db[np.maximum(pv, 0)], 0)
 k = cfg['k']
 pos = np.arange(pu.size) % k
 first_half = np.arange(pu.size) < pu.size // 2
-# light users: no hub business, <= 32 businesses, <= 768 ids walked by the expansion
+# light users: no hub business, <= 32 businesses, <= 512 ids walked (kLightCap) by the expansion
 key = np.unique(eu.astype(np.int64) * cfg['n_biz'] + eb)
 ku, kb = key // cfg['n_biz'], key % cfg['n_biz']
 walked = np.bincount(ku, weights=db[kb].astype(np.float64), minlength=cfg['n_users'])
 hubs_of = np.bincount(ku, weights=(db[kb] >= hub_deg).astype(np.float64), minlength=cfg['n_users'])
-light_user = (hubs_of == 0) & (du <= 32) & (walked <= 768)
+light_user = (hubs_of == 0) & (du <= 32) & (walked <= 512)
 light = light_user[np.maximum(pu, 0)] & (pu >= 0)
 cases = [
     ('light users', light),

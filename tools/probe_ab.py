@@ -2,7 +2,7 @@
 bitmap) on and off, same box, same process.  Times both sides per setting and checks that every
 output column is bit-identical to the path-off run.
 usage: probe_ab.py [CONFIG] [PAIRS] -- settings come from BLP_AB_SETTINGS
-       ("min_deg:ratio:light,..."; min_deg 0 = probe path off, -1 = library default; light 0/1 = the
+       ("min_deg:ratio:light:one_hub_groups,..."; min_deg 0 = probe path off, -1 = library default; light 0/1 = the
        warp-per-group kernel off/on)."""
 import importlib
 import os
@@ -17,21 +17,22 @@ synth = importlib.import_module('bipartite-link-prediction_b200.synth')
 
 name = sys.argv[1] if len(sys.argv) > 1 else 'C2'
 n_pairs = int(sys.argv[2]) if len(sys.argv) > 2 else None
-settings = os.environ.get('BLP_AB_SETTINGS', '0:2:0,-1:2:0,0:2:1,-1:2:1,-1:4:1')
+settings = os.environ.get('BLP_AB_SETTINGS', '0:2:0:0,-1:2:1:0,-1:2:1:1,-1:1:1:1,-1:4:1:1,256:2:1:1')
 cfg, eu, eb, pu, pv = synth.make_config(name, n_pairs=n_pairs)
 du, dv = torch.from_numpy(pu).cuda(), torch.from_numpy(pv).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 base = None
 for s in settings.split(','):
-    min_deg, ratio, light = s.split(':')
+    min_deg, ratio, light, medium = s.split(':')
     os.environ['BLP_LIGHT'] = light
+    os.environ['BLP_LIGHT_HUBS'] = medium
     os.environ.pop('BLP_PROBE_MIN_DEG', None)
     if int(min_deg) >= 0:
         os.environ['BLP_PROBE_MIN_DEG'] = min_deg
     os.environ['BLP_PROBE_RATIO'] = ratio
     G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, device=0)
     info = G.info()
-    res, outs = [], []
+    res, outs, lms = [], [], []
     for side in (0, 1):
         ms, out = [], None
         for it in range(7):
@@ -40,6 +41,7 @@ for s in settings.split(','):
             torch.cuda.synchronize()
             ms.append(G.score_stats(side)['score_ms'])
         res.append(min(ms[1:]))
+        lms.append(G.score_stats(side)['light_ms'])
         outs.append({k: v.clone() for k, v in out.items()})
     same = ''
     if base is None:
@@ -47,6 +49,6 @@ for s in settings.split(','):
     else:
         bad = [(sd, k) for sd in (0, 1) for k in outs[sd] if not torch.equal(outs[sd][k], base[sd][k])]
         same = 'identical to first' if not bad else 'MISMATCH %s' % bad
-    print('light=%s probe_min_deg=%s ratio=%s bitmaps u/b %d/%d  user %.3f ms  business %.3f ms  %s' %
-          (light, min_deg, ratio, info['n_hub_biz'], info['n_hub_users'], res[0], res[1], same), flush=True)
+    print('light=%s one_hub=%s probe_min_deg=%s ratio=%s bitmaps u/b %d/%d  user %.3f ms (light %.3f)  business %.3f ms (light %.3f)  %s' %
+          (light, medium, min_deg, ratio, info['n_hub_biz'], info['n_hub_users'], res[0], lms[0], res[1], lms[1], same), flush=True)
     G.close()
