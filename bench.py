@@ -318,7 +318,7 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     time.sleep(0.3 if sampler else 0.0)
-    total_ms, score_ms_u, score_ms_b, group_ms = 0.0, [], [], []
+    total_ms, score_ms_u, score_ms_b, group_ms, light_ms_u, light_ms_b = 0.0, [], [], [], [], []
     launches = 0
     barrier()
     t_wall0 = time.perf_counter()
@@ -333,6 +333,8 @@ def main():
         su, sb = G.score_stats(_lib.SIDE_USER), G.score_stats(_lib.SIDE_BUSINESS)
         score_ms_u.append(su['score_ms'])
         score_ms_b.append(sb['score_ms'])
+        light_ms_u.append(su['light_ms'])
+        light_ms_b.append(sb['light_ms'])
         group_ms.append(su['group_ms'] + sb['group_ms'])
         launches += su['kernel_launches'] + sb['kernel_launches']
     barrier()
@@ -462,20 +464,28 @@ def main():
         kb_ms = statistics.mean(score_ms_b)
         bytes_u = ab['user'] + ab['pa']
         ach = bytes_u / (ku_ms * 1e-3) / 1e9
-        roof = {'bound': 'hbm', 'kernel': 'k_score_side<user side> (two-hop expansion + '
-                'intersection + epilogue, PA folded in)',
+        roof = {'bound': 'hbm', 'kernel': 'user side = k_score_light (warp per light group) + '
+                'k_score_side (CTA per group), back to back on one stream: two-hop expansion + '
+                'intersection + epilogue, PA folded in',
                 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks
                 else 'fallback 6650 GB/s (of fallback)',
                 'traffic': traffic, 'traffic_source': traffic_src,
                 'algorithmic_bytes_per_launch': bytes_u,
                 'kernel_ms': ku_ms,
-                'business_kernel': {'kernel_ms': kb_ms, 'algorithmic_bytes_per_launch':
+                'kernel_ms_split': {'k_score_light': statistics.mean(light_ms_u),
+                                    'k_score_side': ku_ms - statistics.mean(light_ms_u)},
+                'business_kernel': {'kernel_ms': kb_ms,
+                                    'k_score_light_ms': statistics.mean(light_ms_b),
+                                    'algorithmic_bytes_per_launch':
                                     ab['business'],
                                     'achieved': ab['business'] / (kb_ms * 1e-3) / 1e9},
                 'grouping_ms_per_step': statistics.mean(group_ms),
                 'note': 'graph (26 MB + hub bitmaps) is L2-resident: DRAM traffic is far below the '
-                        'algorithmic bytes; the kernel is latency/L1-bound, see profiles/r01_notes.md.',
+                        'algorithmic bytes; the kernels are latency/issue-bound, and the probe / table '
+                        'paths answer hub-partner pairs without streaming the partner list, so the '
+                        'algorithmic figure credits bytes the implementation does not move -- see '
+                        'profiles/r01_notes.md.',
                 'whole_step': {'algorithmic_bytes': ab['total'],
                                'achieved': ab['total'] / (ms_per_step * 1e-3) / 1e9},
                 'bytes_breakdown': {k: ab[k] for k in ('expansion_user', 'stream_user',

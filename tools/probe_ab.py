@@ -23,7 +23,14 @@ du, dv = torch.from_numpy(pu).cuda(), torch.from_numpy(pv).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 base = None
 for s in settings.split(','):
-    min_deg, ratio, light, medium = s.split(':')
+    min_deg, ratio, light, medium = s.split(':')[:4]
+    extra = s.split(':')[4:]          # optional: hub_min_deg, threads per CTA of the CTA kernel
+    for k in ('BLP_HUB_MIN_DEG', 'BLP_NT'):
+        os.environ.pop(k, None)
+    if len(extra) > 0 and int(extra[0]) > 0:
+        os.environ['BLP_HUB_MIN_DEG'] = extra[0]
+    if len(extra) > 1 and int(extra[1]) > 0:
+        os.environ['BLP_NT'] = extra[1]
     os.environ['BLP_LIGHT'] = light
     os.environ['BLP_LIGHT_HUBS'] = medium
     os.environ.pop('BLP_PROBE_MIN_DEG', None)
@@ -49,6 +56,6 @@ for s in settings.split(','):
     else:
         bad = [(sd, k) for sd in (0, 1) for k in outs[sd] if not torch.equal(outs[sd][k], base[sd][k])]
         same = 'identical to first' if not bad else 'MISMATCH %s' % bad
-    print('light=%s one_hub=%s probe_min_deg=%s ratio=%s bitmaps u/b %d/%d  user %.3f ms (light %.3f)  business %.3f ms (light %.3f)  %s' %
-          (light, medium, min_deg, ratio, info['n_hub_biz'], info['n_hub_users'], res[0], lms[0], res[1], lms[1], same), flush=True)
+    print('%s light=%s one_hub=%s probe_min_deg=%s ratio=%s bitmaps u/b %d/%d  user %.3f ms (light %.3f)  business %.3f ms (light %.3f)  %s' %
+          (':'.join(extra), light, medium, min_deg, ratio, info['n_hub_biz'], info['n_hub_users'], res[0], lms[0], res[1], lms[1], same), flush=True)
     G.close()
