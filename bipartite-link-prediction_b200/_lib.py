@@ -12,7 +12,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, 'csrc')
 INCLUDE = os.path.join(_ROOT, 'include')
 LIB_PATH = os.path.join(_HERE, 'libblp.so')
-SOURCES = ('blp_graph.cu', 'blp_build.cu', 'blp_score.cu', 'blp_hop3.cu', 'blp_eval.cu')
+SOURCES = ('blp_graph.cu', 'blp_build.cu', 'blp_score.cu', 'blp_host.cu', 'blp_hop3.cu', 'blp_eval.cu')
 
 BLP_OK = 0
 BLP_ERR_INVALID, BLP_ERR_CUDA, BLP_ERR_OOM, BLP_ERR_RANGE, BLP_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
@@ -22,7 +22,8 @@ SIDE_USER, SIDE_BUSINESS = 0, 1
 EXPORTS = ('blp_version', 'blp_last_error', 'blp_device_count', 'blp_graph_create',
            'blp_graph_destroy', 'blp_graph_info', 'blp_graph_degrees', 'blp_score_pairs',
            'blp_score_stats', 'blp_graph_reserve_sms', 'blp_graph_create_device',
-           'blp_hop3_count', 'blp_hop3_fill', 'blp_eval_precision_at_k', 'blp_eval_roc_auc')
+           'blp_hop3_count', 'blp_hop3_fill', 'blp_eval_precision_at_k', 'blp_eval_roc_auc',
+           'blp_score_pairs_host')
 
 
 class GraphInfo(ctypes.Structure):
@@ -119,6 +120,8 @@ def load():
     lib.blp_graph_degrees.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     lib.blp_score_pairs.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_int64] + [ctypes.c_void_p] * 7
+    lib.blp_score_pairs_host.argtypes = ([ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int64] + [ctypes.c_void_p] * 9 + [ctypes.c_int] * 3)
     lib.blp_score_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ScoreStats)]
     lib.blp_graph_reserve_sms.argtypes = [ctypes.c_void_p, ctypes.c_int]
     for name in EXPORTS:

@@ -149,6 +149,9 @@ int init_device_state(blp_graph* g, int device) {
     (void)cudaGetLastError();
     for (int sd = 0; sd < 2; ++sd)
         for (int k = 0; k < 4; ++k) BLP_CUDA_TRY(cudaEventCreate(&g->ev[sd][k]));
+    for (int sd = 0; sd < 2; ++sd)
+        BLP_CUDA_TRY(cudaEventCreateWithFlags(&g->ev_fork[sd], cudaEventDisableTiming));
+    BLP_CUDA_TRY(cudaStreamCreateWithFlags(&g->side_stream, cudaStreamNonBlocking));
     return BLP_OK;
 }
 
@@ -321,6 +324,7 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
 extern "C" int blp_graph_destroy(blp_graph* g) {
     if (!g) return BLP_OK;
     cudaSetDevice(g->device);
+    blp::host_state_destroy(g);
     cudaFree(g->u_row);
     cudaFree(g->b_row);
     cudaFree(g->u_adj);
@@ -340,6 +344,9 @@ extern "C" int blp_graph_destroy(blp_graph* g) {
     for (int sd = 0; sd < 2; ++sd)
         for (int k = 0; k < 4; ++k)
             if (g->ev[sd][k]) cudaEventDestroy(g->ev[sd][k]);
+    for (int sd = 0; sd < 2; ++sd)
+        if (g->ev_fork[sd]) cudaEventDestroy(g->ev_fork[sd]);
+    if (g->side_stream) cudaStreamDestroy(g->side_stream);
     (void)cudaGetLastError();
     delete g;
     return BLP_OK;

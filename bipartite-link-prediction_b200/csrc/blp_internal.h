@@ -20,7 +20,10 @@
 // most 1/ln 2 = 1.4427 < 2, so Q1.31 fits 32 bits; sums are kept in 64 bits.
 #define BLP_AA_FRAC_BITS 31
 
+struct blp_host_state;   // staging buffers and streams of blp_score_pairs_host (blp_host.cu)
+
 struct blp_graph {
+    blp_host_state* host = nullptr;
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;  // bytes of dynamic shared memory one CTA may opt in to
@@ -71,6 +74,8 @@ struct blp_graph {
     blp_score_stats_t stats[2] = {};
     cudaEvent_t ev[2][4] = {};   // per side: start, after grouping, after scoring, after the light kernel
     bool ev_light[2] = {false, false};
+    cudaStream_t side_stream = nullptr;          // the warp-per-group kernel runs beside the CTA kernel
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr};
     bool ev_recorded[2] = {false, false};
 };
 
@@ -79,6 +84,7 @@ namespace blp {
 inline int bitmap_words(int n_side) { return (int)((((long long)n_side + 1 + 31) / 32 + 3) & ~3LL); }
 int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host);
 int init_device_state(blp_graph* g, int device);
+void host_state_destroy(blp_graph* g);
 void weight_lut(int32_t max_deg, std::vector<unsigned>& lut);
 int radix_sort_u64(unsigned long long* keys, unsigned long long* tmp, long long n,
                    const std::vector<int>& shifts, cudaStream_t st, unsigned long long** sorted);

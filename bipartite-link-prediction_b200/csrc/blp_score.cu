@@ -2000,17 +2000,18 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
             rc = rec_mode ? launch_side<NTV, RV, true>(a, per_sm * use_sms, smem, st)  \
                           : launch_side<NTV, RV, false>(a, per_sm * use_sms, smem, st); \
     } while (0)
+    // The CTA kernel goes first and the warp-per-group kernel beside it on the handle's side
+    // stream: both are persistent work-queue grids, so as the CTA kernel's blocks retire (its
+    // groups are few and large, the tail is long) the small warp-per-group blocks fill the SMs.
+    // BLP_LIGHT_STREAM=0 keeps both on the caller's stream.
+    bool light_aside = false;
     if (split) {
-        // the warp-per-group kernel first (32 groups in flight per SM)
-        const int lrc =
-            rec_mode ? launch_light<kLightCap, kLightSlots, kLightWarps, true>(g, la, use_sms, st)
-                     : launch_light<kLightCap, kLightSlots, kLightWarps, false>(g, la, use_sms, st);
-        if (lrc != BLP_OK) {
-            release();
-            return lrc;
+        const char* ls = getenv("BLP_LIGHT_STREAM");
+        light_aside = g->side_stream != nullptr && !(ls && atoi(ls) == 0);
+        if (light_aside) {
+            BLP_TRY_SCRATCH(cudaEventRecord(g->ev_fork[side], st));
+            BLP_TRY_SCRATCH(cudaStreamWaitEvent(g->side_stream, g->ev_fork[side], 0));
         }
-        ++launches;
-        g->ev_light[side] = cudaEventRecord(g->ev[side][3], st) == cudaSuccess;
     }
     if (nt == 256) {
         if (ranged) BLP_DISPATCH(256, true); else BLP_DISPATCH(256, false);
@@ -2020,6 +2021,19 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         if (ranged) BLP_DISPATCH(1024, true); else BLP_DISPATCH(1024, false);
     }
 #undef BLP_DISPATCH
+    if (rc == BLP_OK && split) {
+        cudaStream_t lst = light_aside ? g->side_stream : st;
+        rc = rec_mode ? launch_light<kLightCap, kLightSlots, kLightWarps, true>(g, la, use_sms, lst)
+                      : launch_light<kLightCap, kLightSlots, kLightWarps, false>(g, la, use_sms, lst);
+        if (rc == BLP_OK) {
+            ++launches;
+            g->ev_light[side] = cudaEventRecord(g->ev[side][3], lst) == cudaSuccess;
+            // join: everything behind this call on the caller's stream waits for the side stream
+            if (light_aside && cudaStreamWaitEvent(st, g->ev[side][3], 0) != cudaSuccess)
+                rc = blp::cuda_fail(cudaGetLastError(), "joining the side stream", __FILE__, __LINE__);
+        }
+        if (rc != BLP_OK && light_aside) cudaStreamSynchronize(g->side_stream);   // scratch is freed below
+    }
     if (rc == BLP_OK && a.rec) {
         k_unpermute<<<gblocks, 256, 0, st>>>(a.mode, a.rec, inv, n, a.cn, a.uni, a.jac, a.aa);
         if (cudaGetLastError() != cudaSuccess) rc = BLP_ERR_CUDA;

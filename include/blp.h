@@ -137,6 +137,22 @@ int blp_score_pairs(blp_graph* g, int side,
                     int64_t* pa, int32_t* hop2_size, void* stream);
 
 /*
+ * The whole step with HOST buffers: what similarity.main (similarity.py:11-18) does between
+ * loading examples.json and dumping the six score dicts, for array-shaped callers.  pair_u / pair_b
+ * and the nine result columns are HOST arrays of n elements (page-locked memory for full speed;
+ * pageable memory works, slower); the pair ids are uploaded, both sides are scored and every column
+ * is copied back inside the call, which returns when the results are in host memory.  The copies
+ * overlap the kernels: the user side runs in `user_slices` slices, the first `lead_slices` of them
+ * before the rest of the ids are up, the business side in `biz_slices` slices between them
+ * (<= 0 / < 0 / <= 0 select the defaults 5 / 1 / 2).  Outputs as in blp_score_pairs; all are required.
+ * Not re-entrant on one handle (it owns the handle's staging buffers and streams).
+ */
+int blp_score_pairs_host(blp_graph* g, const int32_t* pair_u, const int32_t* pair_b, int64_t n,
+                         int32_t* u_cn, int32_t* u_union, double* u_jaccard, double* u_adamic,
+                         int32_t* b_cn, int32_t* b_union, double* b_jaccard, double* b_adamic,
+                         int64_t* pa, int user_slices, int lead_slices, int biz_slices);
+
+/*
  * Candidate generation: the businesses at BFS distance exactly 3
  * of each given user -- snap.GetNodesAtHop(G, u, 3, ...) of make_examples (dataset_maker.py:137-139),
  * i.e. N(hop2(u)) minus N(u).  Variable-length output, two calls:

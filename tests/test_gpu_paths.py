@@ -127,3 +127,39 @@ def test_light_group_corner_cases(mods, monkeypatch):
                 dict()):
         got, _ = score_with(monkeypatch, graph, env, n_users, n_biz, eu, eb, pu, pv)
         check_against(got, want, pu.size)
+
+
+def test_host_buffer_entry_point(mods):
+    """blp_score_pairs_host (host buffers in and out, copies inside the call) == the device call,
+    for pinned session buffers, for plain pageable numpy arrays, and for every slice plan."""
+    import ctypes
+    graph, synth = mods
+    lib_mod = pkg('_lib')
+    cfg, eu, eb, pu, pv = synth.make_config('C1', n_pairs=100_000)
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    want = G.score_pairs_host(pu, pv)            # device call + explicit copies
+    n = pu.size
+    sess = G.host_session(n)
+    for plan in ((0, -1, 0), (1, 0, 1), (3, 2, 1), (7, 1, 4)):
+        got = sess.score(pu, pv) if plan == (0, -1, 0) else None
+        if got is None:
+            hu, hb = sess.pinned_inputs(n)
+            hu[:] = pu
+            hb[:] = pv
+            got = sess.score_pinned(n, *plan)
+        for k in sess.KEYS:
+            assert np.array_equal(got[k], want[k]), (plan, k)
+    # pageable memory straight through ctypes
+    cols = [np.empty(n, dt) for dt in (np.int32, np.int32, np.float64, np.float64) * 2] + [np.empty(n, np.int64)]
+    pu_c, pv_c = np.ascontiguousarray(pu), np.ascontiguousarray(pv)
+    rc = G._lib.blp_score_pairs_host(G._h, pu_c.ctypes.data, pv_c.ctypes.data, n,
+                                     *[c.ctypes.data for c in cols], 0, -1, 0)
+    assert rc == lib_mod.BLP_OK
+    for k, c in zip(sess.KEYS, cols):
+        assert np.array_equal(c, want[k]), k
+    # argument checking: a missing output column is refused, n = 0 is a no-op
+    bad = [c.ctypes.data for c in cols]
+    bad[3] = None
+    assert G._lib.blp_score_pairs_host(G._h, pu_c.ctypes.data, pv_c.ctypes.data, n, *bad, 0, -1, 0) \
+        == lib_mod.BLP_ERR_INVALID
+    assert G._lib.blp_score_pairs_host(G._h, None, None, 0, *([None] * 9), 0, -1, 0) == lib_mod.BLP_OK

@@ -11,12 +11,20 @@ n = pu.size
 sess = G.host_session(n)
 hu, hb = sess.pinned_inputs(n)
 hu[:] = pu; hb[:] = pv
-for chunks, lead in ((4, 0), (8, 0), (8, 1), (8, 2), (8, 3), (16, 3), (16, 5), (12, 3)):
-    for _ in range(2):
-        sess.score_pinned(n, user_chunks=chunks, lead_chunks=lead)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(8):
-        sess.score_pinned(n, user_chunks=chunks, lead_chunks=lead)
-    dt = (time.perf_counter() - t0) / 8
-    print('chunks %2d lead %d: %.2f ms  -> %.0f M pairs/s' % (chunks, lead, dt * 1e3, n / dt / 1e6), flush=True)
+import numpy as np
+ref = {k: v.copy() for k, v in sess.score_pinned_py(n).items()}
+for fn, name, growth in ((sess.score_pinned, 'native, equal slices', '1.0'), (sess.score_pinned, 'native, growth 1.5', '1.5'),
+                         (sess.score_pinned, 'native, growth 2', '2.0'), (sess.score_pinned_py, 'python pipeline', '1')):
+    os.environ['BLP_SLICE_GROWTH'] = growth
+    for chunks, lead, biz in ((4, 1, 2), (5, 1, 2), (6, 1, 2), (6, 2, 2), (8, 2, 2), (4, 1, 1)):
+        for _ in range(2):
+            out = fn(n, user_chunks=chunks, lead_chunks=lead, biz_chunks=biz)
+        same = all(np.array_equal(out[k], ref[k]) for k in ref)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(8):
+            fn(n, user_chunks=chunks, lead_chunks=lead, biz_chunks=biz)
+        dt = (time.perf_counter() - t0) / 8
+        print('%-28s user slices %2d lead %d biz slices %d: %.2f ms  -> %.0f M pairs/s  %s' %
+              (name, chunks, lead, biz, dt * 1e3, n / dt / 1e6, 'same results' if same else 'MISMATCH'),
+              flush=True)
