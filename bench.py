@@ -474,6 +474,9 @@ def main():
                 'algorithmic_bytes_per_launch': bytes_u,
                 'kernel_ms': ku_ms,
                 'k_score_light_span_ms': statistics.mean(light_ms_u),
+                'work_items': {'user_side': su['n_groups'], 'user_side_warp_kernel': su['light_groups'],
+                               'business_side': sb['n_groups'],
+                               'business_side_warp_kernel': sb['light_groups']},
                 'business_kernel': {'kernel_ms': kb_ms,
                                     'k_score_light_ms': statistics.mean(light_ms_b),
                                     'algorithmic_bytes_per_launch':

@@ -45,7 +45,8 @@ class ScoreStats(ctypes.Structure):
                 ('kernel_launches', ctypes.c_int32), ('ctas', ctypes.c_int32),
                 ('threads_per_cta', ctypes.c_int32), ('smem_bytes', ctypes.c_int32),
                 ('range_passes', ctypes.c_int32), ('group_ms', ctypes.c_float),
-                ('score_ms', ctypes.c_float), ('light_ms', ctypes.c_float)]
+                ('score_ms', ctypes.c_float), ('light_ms', ctypes.c_float),
+                ('light_groups', ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -152,6 +152,10 @@ int init_device_state(blp_graph* g, int device) {
     for (int sd = 0; sd < 2; ++sd)
         BLP_CUDA_TRY(cudaEventCreateWithFlags(&g->ev_fork[sd], cudaEventDisableTiming));
     BLP_CUDA_TRY(cudaStreamCreateWithFlags(&g->side_stream, cudaStreamNonBlocking));
+    for (int sd = 0; sd < 2; ++sd) {
+        BLP_CUDA_TRY(cudaMalloc((void**)&g->d_counts[sd], sizeof(int) * 2));
+        BLP_CUDA_TRY(cudaMemset(g->d_counts[sd], 0, sizeof(int) * 2));
+    }
     return BLP_OK;
 }
 
@@ -347,6 +351,7 @@ extern "C" int blp_graph_destroy(blp_graph* g) {
     for (int sd = 0; sd < 2; ++sd)
         if (g->ev_fork[sd]) cudaEventDestroy(g->ev_fork[sd]);
     if (g->side_stream) cudaStreamDestroy(g->side_stream);
+    for (int sd = 0; sd < 2; ++sd) cudaFree(g->d_counts[sd]);
     (void)cudaGetLastError();
     delete g;
     return BLP_OK;
@@ -409,6 +414,10 @@ extern "C" int blp_score_stats(const blp_graph* g, int side, blp_score_stats_t* 
         BLP_CUDA_TRY(cudaEventElapsedTime(&stats->score_ms, g->ev[side][1], g->ev[side][2]));
         if (g->ev_light[side])
             BLP_CUDA_TRY(cudaEventElapsedTime(&stats->light_ms, g->ev[side][1], g->ev[side][3]));
+        int counts[2] = {0, 0};
+        BLP_CUDA_TRY(cudaMemcpy(counts, g->d_counts[side], sizeof(counts), cudaMemcpyDeviceToHost));
+        stats->n_groups = counts[0];
+        stats->light_groups = counts[1];
     }
     return BLP_OK;
 }

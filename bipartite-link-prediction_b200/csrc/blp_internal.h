@@ -74,6 +74,7 @@ struct blp_graph {
     blp_score_stats_t stats[2] = {};
     cudaEvent_t ev[2][4] = {};   // per side: start, after grouping, after scoring, after the light kernel
     bool ev_light[2] = {false, false};
+    int* d_counts[2] = {nullptr, nullptr};       // per side: work items, light items of the last call
     cudaStream_t side_stream = nullptr;          // the warp-per-group kernel runs beside the CTA kernel
     cudaEvent_t ev_fork[2] = {nullptr, nullptr};
     bool ev_recorded[2] = {false, false};

@@ -15,6 +15,14 @@
 // cut into 512-id chunks, the chunk counts are prefix-summed in shared memory and warps take
 // chunks round-robin, so a hub list is spread over the whole CTA while short lists cost one
 // warp pass each (degree-bucketed scheduling without separate launches).
+//
+// Layout of the translation unit:
+//   blp_score_common.cuh  launch arguments (SideArgs), row-descriptor accessors, streaming loads
+//   blp_score_group.cuh   pairs -> work items (runs / counting sort), light / heavy split
+//   blp_score_light.cuh   k_score_light: one WARP per small group (hash-table hop-2 set), the
+//                         per-node class flags and the hub x bitmap-node intersection tables
+//   this file             k_score_side: one CTA per group (shared-memory bitmap), hub-bitmap
+//                         construction, blp_score_pairs (grouping, split, both launches)
 #include <algorithm>
 #include <climits>
 #include <cstdio>
@@ -24,330 +32,15 @@
 
 #include "blp_internal.h"
 
+#include "blp_score_common.cuh"
+#include "blp_score_group.cuh"
+#include "blp_score_light.cuh"
+
 namespace blp {
-
-#ifndef BLP_TILE
-#define BLP_TILE 256
-#endif
-constexpr int kTile = BLP_TILE;   // adjacency lists per scheduling tile (<= threads per CTA)
-#ifndef BLP_CHUNK_V4
-#define BLP_CHUNK_V4 128
-#endif
-constexpr int kChunkV4 = BLP_CHUNK_V4;   // int4 loads per chunk (at most 4 per lane): 512 ids
-constexpr unsigned kFull = 0xffffffffu;
-
-struct SideArgs {
-    // grouping side x: rows x -> middle nodes m;   middle side: rows m -> nodes of x's side.
-    // A row descriptor packs (first entry / 4) << 24 | degree: one 8-byte load locates a list.
-    const unsigned long long* __restrict__ g_row;
-    const int* __restrict__ g_adj;
-    const unsigned long long* __restrict__ m_row;
-    const int* __restrict__ m_adj;
-    const unsigned* __restrict__ m_adjw;  // Q1.31 Adamic-Adar weight of every m_adj entry
-    int n_side;                           // number of x-side nodes == sentinel id of m rows
-    int bm_words;                         // bitmap words (covers bit n_side as well)
-    // hub bitmaps: N(m) of every middle node with deg >= hub_min_deg, as bm_words-word bitmaps
-    // m_xrow: row descriptors as seen by the expansion -- equal to m_row except that a hub's
-    // entry is  1<<63 | bitmap slot << 24 | degree  (one gather tells list from bitmap)
-    const unsigned long long* __restrict__ m_xrow;
-    const unsigned* __restrict__ hub_bm;
-    int hub_words;                        // words per hub bitmap (whole id universe)
-    // probe path of the intersection: Q1.31 weight of every x-side node (null = path off)
-    const unsigned* __restrict__ node_wt;
-    int probe_ratio;
-    // |N(h) & N(y)| and the weight sum over it for every OR-hub h (row) and bitmap node y (column):
-    // lets the warp-per-group kernel take groups with ONE hub without touching the hub's bitmap
-    const int* __restrict__ hubtab_cn;
-    const unsigned long long* __restrict__ hubtab_aa;
-    int hubtab_stride;
-    // id-range passes: when the bitmap of the whole universe does not fit (or is not wanted) in
-    // shared memory the group is processed n_ranges times, pass r covering ids
-    // [r*range_bits, (r+1)*range_bits); partial cn / aa wait in scratch (grouped order)
-    int range_bits;
-    int n_ranges;
-    int* acc_cn;
-    unsigned long long* acc_aa;
-    // grouping
-    // work items: item i is the node item_key[i] (n_side = "not in graph") with the pairs
-    // [item_start[i], item_end[i]) of the grouped order
-    const int* __restrict__ item_key;
-    const int* __restrict__ item_start;
-    const int* __restrict__ item_end;
-    const int* __restrict__ n_items;
-    // with the light / heavy split (k_split_items) each scoring kernel walks its own list of item
-    // indices: position i of the persistent loop is item item_list[i]; null = every item in order
-    const int* __restrict__ item_list;
-    const int2* __restrict__ pg;            // sort mode: (caller-order pair index, partner y) per
-                                            // grouped position -- one 8-byte scattered store
-    const int* __restrict__ mode;           // MODE_RUNS: grouped order == caller order, pg is
-    const int* __restrict__ caller_y;       //            unused and the partners are caller_y
-    int* work_counter;
-    // sort mode only: results are first written as 24-byte records in GROUPED order (coalesced)
-    // and brought to the caller's order by k_unpermute; null = write the outputs directly
-    unsigned long long* rec;
-    // outputs, caller order (any may be null)
-    int* cn;
-    int* uni;
-    double* jac;
-    double* aa;
-    long long* pa;
-    int* hop2;
-};
-
-__device__ __forceinline__ int4 ldg_stream(const int4* p) {
-    int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
-__device__ __forceinline__ int row_deg(unsigned long long row) { return (int)(row & 0xffffffull); }
-__device__ __forceinline__ long long row_first4(unsigned long long row) {
-    return (long long)((row >> 24) & ((1ull << BLP_ROW_FIRST4_BITS) - 1));
-}
-// hub-bitmap slot + 1 of the node the row belongs to (0 = its list has no bitmap); bit 63 is the
-// expansion-side hub flag of m_xrow and is not part of the field
-__device__ __forceinline__ int row_slot1(unsigned long long row) {
-    return (int)((row >> BLP_ROW_SLOT_SHIFT) & (unsigned long long)BLP_ROW_MAX_SLOTS);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Grouping.  Every pair gets a key: the node whose hop-2 set it needs, or n_side when an id of
-// the pair is not in the graph.  Two ways to turn keys into work items:
-//   runs   -- the pairs already arrive grouped (examples.json stores them per user): every run
-//             of equal keys is an item, the grouped order is the caller order, nothing moves;
-//   sort   -- counting sort of the pair indices by key (any order in, e.g. the business side).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int group_key(int x, int y, int n_side, int n_mid,
-                                         const int* __restrict__ g_deg,
-                                         const int* __restrict__ m_deg) {
-    bool ok = x >= 0 && x < n_side && y >= 0 && y < n_mid;
-    if (ok) ok = (g_deg[x] > 0) && (m_deg[y] > 0);
-    return ok ? x : n_side;   // similarity.py:52,59-60: any id not in the graph -> literal 0
-}
-
-__global__ void k_group_keys(const int* __restrict__ gx, const int* __restrict__ gy, long long n,
-                             int n_side, int n_mid, const int* __restrict__ g_deg,
-                             const int* __restrict__ m_deg, int* __restrict__ keys) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) keys[i] = group_key(gx[i], gy[i], n_side, n_mid, g_deg, m_deg);
-}
-
-constexpr int kRunCut = 4096;   // runs are cut at multiples of this, bounding the serial scan below
-
-__device__ __forceinline__ bool run_starts_at(const int* __restrict__ keys, long long i) {
-    return i == 0 || (i % kRunCut) == 0 || keys[i] != keys[i - 1];
-}
-
-__global__ void k_count_runs(const int* __restrict__ keys, long long n, unsigned* __restrict__ n_runs) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long stride = (long long)gridDim.x * blockDim.x;
-    unsigned c = 0;
-    for (; i < n; i += stride) c += run_starts_at(keys, i);
-    c = __reduce_add_sync(kFull, c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_runs, c);
-}
-
-// Grouping mode, decided on the device so that the call never waits for the host:
-// runs are used when they average >= 4 pairs (BLP_GROUPING=runs/sort forces a mode).
-enum { MODE_SORT = 0, MODE_RUNS = 1 };
-__global__ void k_decide_mode(const unsigned* __restrict__ n_runs, long long n, int force,
-                              int* __restrict__ mode) {
-    *mode = force >= 0 ? force : (((long long)*n_runs * 4 <= n) ? MODE_RUNS : MODE_SORT);
-}
-
-// One CTA per kRunCut-sized segment of the pair list (runs never cross a segment boundary):
-// every thread owns 16 consecutive positions, a block scan numbers the run starts, the item slots
-// of the segment are claimed with one atomic, and a run's end is the next run's start.
-__global__ void __launch_bounds__(256) k_runs_to_items(const int* __restrict__ mode,
-                                                       const int* __restrict__ keys, long long n,
-                                                       int* __restrict__ item_key,
-                                                       int* __restrict__ item_start,
-                                                       int* __restrict__ item_end,
-                                                       int* __restrict__ n_items) {
-    if (*mode != MODE_RUNS) return;
-    static_assert(kRunCut == 256 * 16, "one thread owns 16 positions of a segment");
-    __shared__ int s_warp[8];
-    __shared__ int s_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long n_seg = (n + kRunCut - 1) / kRunCut;
-    for (long long seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
-        const long long seg_lo = seg * kRunCut, seg_hi = min(n, seg_lo + kRunCut);
-        const long long lo = seg_lo + tid * 16;
-        int k[17];
-        k[0] = (lo > seg_lo && lo - 1 < seg_hi) ? keys[lo - 1] : INT_MIN;   // INT_MIN: forces a start
-#pragma unroll
-        for (int j = 0; j < 16; ++j) k[j + 1] = lo + j < seg_hi ? keys[lo + j] : INT_MIN;
-        int mine = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) mine += (lo + j < seg_hi) && (k[j + 1] != k[j]);
-        int inc = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(kFull, inc, d);
-            if (lane >= d) inc += t;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        int before = inc - mine, total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            if (w < warp) before += s_warp[w];
-            total += s_warp[w];
-        }
-        if (tid == 0) s_base = atomicAdd(n_items, total);
-        __syncthreads();
-        int slot = s_base + before;
-        const int last = s_base + total - 1;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (lo + j < seg_hi && k[j + 1] != k[j]) {
-                item_key[slot] = k[j + 1];
-                item_start[slot] = (int)(lo + j);
-                if (slot > s_base) item_end[slot - 1] = (int)(lo + j);
-                ++slot;
-            }
-        }
-        if (tid == 0 && total > 0) item_end[last] = (int)seg_hi;
-        __syncthreads();
-    }
-}
-
-__global__ void k_group_count(const int* __restrict__ mode, const int* __restrict__ keys,
-                              long long n, unsigned* __restrict__ cnt) {
-    if (*mode != MODE_SORT) return;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) atomicAdd(&cnt[keys[i]], 1u);
-}
-
-// Single-CTA exclusive scan of the group sizes; also compacts the non-empty keys into items.
-// Four keys per thread and iteration (4096 per trip) keep the serial trip count low.
-__global__ void __launch_bounds__(1024) k_group_scan(const int* __restrict__ mode,
-                                                     const unsigned* __restrict__ cnt, int n_keys,
-                                                     unsigned* __restrict__ grp_off,
-                                                     int* __restrict__ item_key,
-                                                     int* __restrict__ item_start,
-                                                     int* __restrict__ item_end,
-                                                     int* __restrict__ n_items) {
-    if (*mode != MODE_SORT) return;
-    __shared__ unsigned s_sum[32];
-    __shared__ int s_flag[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned base = 0;   // carried identically by every thread (n < 2^31 pairs per call)
-    int fbase = 0;
-    for (int start = 0; start < n_keys; start += 4096) {
-        const int i0 = start + tid * 4;
-        unsigned c[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) c[k] = i0 + k < n_keys ? cnt[i0 + k] : 0u;
-        unsigned v = c[0] + c[1] + c[2] + c[3];
-        int f = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
-        const unsigned own_v = v;
-        const int own_f = f;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned t = __shfl_up_sync(kFull, v, d);
-            int tf = __shfl_up_sync(kFull, f, d);
-            if (lane >= d) {
-                v += t;
-                f += tf;
-            }
-        }
-        if (lane == 31) {
-            s_sum[warp] = v;
-            s_flag[warp] = f;
-        }
-        __syncthreads();
-        unsigned wv = s_sum[lane];
-        int wf = s_flag[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned t = __shfl_up_sync(kFull, wv, d);
-            int tf = __shfl_up_sync(kFull, wf, d);
-            if (lane >= d) {
-                wv += t;
-                wf += tf;
-            }
-        }
-        const unsigned trip_total = __shfl_sync(kFull, wv, 31);
-        const int trip_flags = __shfl_sync(kFull, wf, 31);
-        unsigned wb = __shfl_sync(kFull, wv, max(warp, 1) - 1);
-        int fb = __shfl_sync(kFull, wf, max(warp, 1) - 1);
-        if (warp == 0) {
-            wb = 0;
-            fb = 0;
-        }
-        unsigned off = base + wb + (v - own_v);          // exclusive prefix of this thread
-        int slot = fbase + fb + (f - own_f);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < n_keys) {
-                grp_off[i0 + k] = off;                   // doubles as the scatter cursor
-                if (c[k] > 0) {
-                    item_key[slot] = i0 + k;
-                    item_start[slot] = (int)off;
-                    item_end[slot] = (int)(off + c[k]);
-                    ++slot;
-                }
-                off += c[k];
-            }
-        }
-        base += trip_total;
-        fbase += trip_flags;
-        __syncthreads();
-    }
-    if (tid == 0) *n_items = fbase;
-}
-
-__global__ void k_group_scatter(const int* __restrict__ mode, const int* __restrict__ keys,
-                                const int* __restrict__ gy, long long n,
-                                unsigned* __restrict__ cursor, int2* __restrict__ pg,
-                                int* __restrict__ inv) {
-    if (*mode != MODE_SORT) return;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        const unsigned pos = atomicAdd(&cursor[keys[i]], 1u);   // cursor starts at the group offset
-        pg[pos] = make_int2((int)i, gy[i]);
-        inv[i] = (int)pos;
-    }
-}
-
-// Sort mode, second half: grouped-order records -> caller-order columns.  A gather through the
-// inverse permutation: random 24-byte reads are far cheaper than the random 4/8-byte partial-
-// sector writes the scoring kernel would otherwise issue (measured: 0.8 ms of 2.4 ms on C2).
-__global__ void k_unpermute(const int* __restrict__ mode, const unsigned long long* __restrict__ rec,
-                            const int* __restrict__ inv, long long n, int* __restrict__ cn,
-                            int* __restrict__ uni, double* __restrict__ jac, double* __restrict__ aa) {
-    if (*mode != MODE_SORT) return;
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        const unsigned long long* r = rec + 3ll * inv[i];
-        const unsigned long long c = r[0];
-        if (cn) cn[i] = (int)(unsigned)c;
-        if (uni) uni[i] = (int)(unsigned)(c >> 32);
-        if (jac) jac[i] = __longlong_as_double((long long)r[1]);
-        if (aa) aa[i] = __longlong_as_double((long long)r[2]);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // The scoring kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int kShortV4 = 4;   // lists of <= 16 ids take the sub-warp path (4 lanes per list)
-// Probe path.  A hop-2 set built from at most kProbeCap list entries and no hub bitmap is also
-// kept as an id list (the atomicOr that turns a bit on appends the id).  A pair of that group
-// whose partner y has a bitmap and deg(y) >= probe_ratio * |hop2(x)| is then scored by probing
-// y's bitmap with the list -- |hop2(x)| global loads instead of streaming deg(y) ids + weights.
-// On C2 this replaces ~45 % of all streamed ids by ~5 % as many probes (hub partners are drawn
-// in proportion to their degree; two thirds of the users have no hub business and a small set).
-constexpr int kProbeCap = 768;
-constexpr int kProbeRatio = 2;   // default; BLP_PROBE_RATIO overrides it at graph creation
-
 struct TileSmem {
     unsigned long long row[kTile];     // packed row descriptor of every list of the tile
     unsigned long long aa[kTile];      // Q24.40 Adamic-Adar accumulators
@@ -432,14 +125,6 @@ __device__ __forceinline__ int find_list(const TileSmem& ts, int c, int lane) {
     int kb = __popc(__ballot_sync(kFull, v <= c)) - 1;
     int v2 = lane < 8 ? ts.scan[kb * 8 + lane] : INT_MAX;
     return kb * 8 + __popc(__ballot_sync(kFull, v2 <= c)) - 1;
-}
-
-__device__ __forceinline__ uint4 ldg_stream_u(const uint4* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
 }
 
 // The two things done to a streamed id.
@@ -729,11 +414,6 @@ __device__ __forceinline__ void stage1(const SideArgs& a, GroupRegs& g, int n_it
 }
 __device__ __forceinline__ void stage2(const SideArgs& a, GroupRegs& g) {
     g.xrow = g.x < a.n_side ? a.g_row[g.x] : 0ull;
-}
-
-// (caller-order index, partner) of the pair at grouped position k
-__device__ __forceinline__ int2 pair_at(const SideArgs& a, long long k) {
-    return a.pg ? a.pg[k] : make_int2((int)k, a.caller_y[k]);
 }
 
 template <int NT, bool RANGED, bool REC>
@@ -1033,557 +713,6 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
     }
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// Light groups: one WARP per group.
-//
-// Measured on C2 (tools/cost_model.py): 60 % of the CTA kernel's time is per-GROUP cost -- a
-// chain of ~8 CTA barriers and ~6 dependent global round trips per group with only four groups in
-// flight per SM (four 46 KB bitmaps) -- and about half of the groups are tiny: a user with a few
-// small businesses whose expansion walks a few hundred ids.  Such a group (classified per node at
-// graph creation: <= 32 middle nodes, none of them an OR-hub, <= CAP ids walked) needs no bitmap
-// over the whole universe.  Here one warp owns it: hop2(x) goes into an open-addressing hash
-// table in shared memory (and, in insertion order, into an id list), the partner lists are
-// streamed against the table -- all lists of a 32-pair tile as ONE flattened index space, so that
-// short lists cost no pass of their own and every lane has loads in flight -- and partners that
-// have a bitmap are scored by probing it with the list.  No CTA barrier anywhere; the descriptor
-// chain of the next group is fetched in stages behind the current group's phases.  The arithmetic
-// is the same integer arithmetic as in k_score_side, so the outputs are bit-identical.
-// A group with exactly ONE hub among its middle nodes qualifies as well: hop2(x) = N(h) + S' with
-// S' = the ids of the other lists that are not in N(h); the table and the list hold S' only, a
-// streamed id that misses the table is looked up in the hub's bitmap where it lies (L2), and for a
-// partner y that has a bitmap itself |N(h) & N(y)| comes from a table precomputed at graph creation.
-// (A larger-table "medium" instance with 8 groups in flight per SM was measured and is slower than
-// the CTA kernel: one warp streaming a hub partner's list is too slow.)
-// ---------------------------------------------------------------------------------------------
-constexpr int kLightCap = 512, kLightSlots = 1024, kLightWarps = 8;
-constexpr int kLightEmpty = -1;
-
-template <int CAP, int SLOTS>
-struct LightSmem {
-    int table[SLOTS];
-    int list[CAP];
-    // per pair of the tile: hits and weighted hits.  The weight sum is kept as two 32-bit words
-    // (low 24 bits / the rest) so that native 32-bit shared atomics add it exactly: a lane adds
-    // its whole share of a pair at once (<= 32 adds per pair), and a pair has < 2^24 hits.
-    unsigned aa_lo[32];
-    unsigned aa_hi[32];
-    int cn[32];
-};
-
-// The table is a set of 4-slot buckets (16 bytes, one 128-bit shared load).  A bucket fills from
-// slot 0 upwards, so it is full exactly when its last slot is taken; only then does a search go on
-// to the next bucket.  At the typical load (~0.2) a lookup is one load and four compares, with
-// hardly any divergence between the lanes.
-template <int SLOTS>
-__device__ __forceinline__ unsigned light_bucket(int id) {
-    static_assert((SLOTS & (SLOTS - 1)) == 0 && SLOTS >= 64, "power of two");
-    return (((unsigned)id * 2654435761u) >> 8) & (unsigned)(SLOTS / 4 - 1);
-}
-
-template <int SLOTS>
-__device__ __forceinline__ bool light_has(const int* table, int id) {
-    unsigned b = light_bucket<SLOTS>(id);
-    while (true) {
-        const int4 v = reinterpret_cast<const int4*>(table)[b];
-        if (v.x == id || v.y == id || v.z == id || v.w == id) return true;
-        if (v.w == kLightEmpty) return false;   // bucket not full (the padding id ends here too)
-        b = (b + 1) & (SLOTS / 4 - 1);
-    }
-}
-
-// true when THIS call put the id into the table
-template <int SLOTS>
-__device__ __forceinline__ bool light_insert(int* table, int id) {
-    unsigned b = light_bucket<SLOTS>(id);
-    while (true) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int prev = atomicCAS(&table[4 * b + k], kLightEmpty, id);
-            if (prev == kLightEmpty) return true;
-            if (prev == id) return false;
-        }
-        b = (b + 1) & (SLOTS / 4 - 1);
-    }
-}
-
-// expansion step for the four ids of one 128-bit load; new ids are appended to the list with one
-// ballot per component (list_n is warp-uniform)
-__device__ __forceinline__ bool hub_bit(const unsigned* hbm, int id) {
-    return (__ldg(hbm + (id >> 5)) >> (id & 31)) & 1u;
-}
-
-// hbm: bitmap of the group's single hub (null = none); ids already in it stay out of the table
-template <int SLOTS>
-__device__ __forceinline__ void light_expand4(int* table, int* list, int4 v, bool active, int x,
-                                              int n_side, const unsigned* hbm, int& list_n, int lane) {
-    const int id[4] = {v.x, v.y, v.z, v.w};
-    bool want[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) want[k] = active && id[k] < n_side && id[k] != x;
-    if (hbm) {
-        bool in_hub[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) in_hub[k] = want[k] && hub_bit(hbm, id[k]);   // four loads in flight
-#pragma unroll
-        for (int k = 0; k < 4; ++k) want[k] = want[k] && !in_hub[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const bool fresh = want[k] && light_insert<SLOTS>(table, id[k]);
-        const unsigned m = __ballot_sync(kFull, fresh);
-        if (fresh) list[list_n + __popc(m & ((1u << lane) - 1u))] = id[k];
-        list_n += __popc(m);
-    }
-}
-
-template <int SLOTS>
-__device__ __forceinline__ void light_test4(const int* table, int4 v, uint4 wt, int x,
-                                            const unsigned* hbm, unsigned& cnt,
-                                            unsigned long long& acc) {
-    const int id[4] = {v.x, v.y, v.z, v.w};
-    const unsigned w[4] = {wt.x, wt.y, wt.z, wt.w};
-    bool hit[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) hit[k] = light_has<SLOTS>(table, id[k]);
-    if (hbm) {   // hop2(x) also holds N(h) \ {x}; bit n_side (the padding id) is never on
-        bool in_hub[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) in_hub[k] = !hit[k] && id[k] != x && hub_bit(hbm, id[k]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) hit[k] = hit[k] || in_hub[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (hit[k]) {
-            ++cnt;
-            acc += w[k];
-        }
-}
-
-// exact warp sum of per-lane weight sums (three 16/16/32-bit limbs, REDUX each)
-__device__ __forceinline__ unsigned long long light_sum64(unsigned long long acc) {
-    const unsigned l0 = __reduce_add_sync(kFull, (unsigned)(acc & 0xffffull));
-    const unsigned l1 = __reduce_add_sync(kFull, (unsigned)((acc >> 16) & 0xffffull));
-    const unsigned l2 = __reduce_add_sync(kFull, (unsigned)(acc >> 32));
-    return ((unsigned long long)l2 << 32) + ((unsigned long long)l1 << 16) + l0;
-}
-
-__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(kFull, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-
-// Flattened lists: lane l holds the inclusive prefix of the lengths.  Which lane's list owns the
-// flat index i (< total)?  = number of lanes whose inclusive prefix is <= i.
-__device__ __forceinline__ int seg_search(int incl, int i) {
-    int lo = 0;
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const int t = __shfl_sync(kFull, incl, lo + s - 1);
-        if (t <= i) lo += s;
-    }
-    return lo;
-}
-
-// descriptor chain of one group, fetched in stages (every field warp-uniform except m / mrow)
-struct LightRegs {
-    int it;                     // item index, -1 = none
-    int x;
-    int p0, p1;
-    unsigned long long xrow;
-    int m;                      // lane < deg(x): this lane's middle node
-    unsigned long long mrow;    // ... and its row
-};
-__device__ __forceinline__ void light_stage_a(const SideArgs& a, LightRegs& g, int c, int n_items) {
-    g.it = c < n_items ? a.item_list[c] : -1;
-}
-__device__ __forceinline__ void light_stage_b(const SideArgs& a, LightRegs& g) {
-    g.x = 0;
-    g.p0 = g.p1 = 0;
-    if (g.it >= 0) {
-        g.x = a.item_key[g.it];
-        g.p0 = a.item_start[g.it];
-        g.p1 = a.item_end[g.it];
-    }
-}
-__device__ __forceinline__ void light_stage_c(const SideArgs& a, LightRegs& g) {
-    g.xrow = g.it >= 0 ? a.g_row[g.x] : 0ull;
-}
-__device__ __forceinline__ void light_stage_d(const SideArgs& a, LightRegs& g, int lane) {
-    g.m = lane < row_deg(g.xrow) ? a.g_adj[row_first4(g.xrow) * 4 + lane] : -1;
-}
-__device__ __forceinline__ void light_stage_e(const SideArgs& a, LightRegs& g) {
-    g.mrow = g.m >= 0 ? a.m_xrow[g.m] : 0ull;   // a hub's entry carries flag, slot and table row
-}
-
-template <int CAP, int SLOTS, int WARPS, bool REC>
-__global__ void __launch_bounds__(WARPS * 32, 2048 / (WARPS * 32) / 2) k_score_light(SideArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    typedef LightSmem<CAP, SLOTS> Smem;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Smem& ls = reinterpret_cast<Smem*>(smem_raw)[warp];
-    const int n_items = *a.n_items;
-    if (*a.mode == MODE_RUNS) a.pg = nullptr;
-    const int4* adj4 = reinterpret_cast<const int4*>(a.m_adj);
-    const uint4* adjw4 = reinterpret_cast<const uint4*>(a.m_adjw);
-    const int4 sent4 = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
-    const int4 empty4 = make_int4(kLightEmpty, kLightEmpty, kLightEmpty, kLightEmpty);
-    {
-        int4* t4 = reinterpret_cast<int4*>(ls.table);
-        for (int i = lane; i < SLOTS / 4; i += 32) t4[i] = empty4;
-    }
-    __syncwarp();
-    // two claims ahead: the index of the next group is known when the current one starts
-    int c = 0, c1 = 0;
-    if (lane == 0) {
-        c = atomicAdd(a.work_counter, 1);
-        c1 = atomicAdd(a.work_counter, 1);
-    }
-    c = __shfl_sync(kFull, c, 0);
-    c1 = __shfl_sync(kFull, c1, 0);
-    LightRegs cur;
-    light_stage_a(a, cur, c, n_items);
-    light_stage_b(a, cur);
-    light_stage_c(a, cur);
-    light_stage_d(a, cur, lane);
-    light_stage_e(a, cur);
-    while (c < n_items) {
-        int c2 = 0;
-        if (lane == 0) c2 = atomicAdd(a.work_counter, 1);
-        LightRegs nxt;
-        light_stage_a(a, nxt, c1, n_items);
-        const int x = cur.x;
-        const long long p0 = cur.p0, p1 = cur.p1;
-        const int xdeg = row_deg(cur.xrow);   // 1..32 by the class flag
-        // partners of the first pair tile: issued now, their rows after the expansion
-        int2 iy0 = make_int2(0, 0);
-        if (p0 + lane < p1) iy0 = pair_at(a, p0 + lane);
-        // the group's hub, if it has one (at most one, by its class)
-        const unsigned hub_lanes = __ballot_sync(kFull, (cur.mrow >> 63) != 0);
-        const unsigned* hbm = nullptr;
-        int hub_deg = 0, hub_tab = 0;
-        if (hub_lanes) {
-            const unsigned long long hr = __shfl_sync(kFull, cur.mrow, __ffs(hub_lanes) - 1);
-            hbm = a.hub_bm + (size_t)((hr >> 24) & (unsigned long long)BLP_ROW_MAX_SLOTS) * (size_t)a.hub_words;
-            hub_deg = row_deg(hr);
-            hub_tab = (int)((hr >> BLP_XROW_ORIDX_SHIFT) & (unsigned long long)BLP_ROW_MAX_SLOTS) *
-                      a.hubtab_stride;
-        }
-        // ---- expansion: the lists N(m), m in N(x), as one flattened space of 128-bit loads
-        int list_n = 0;
-        {
-            const int mn4 = (cur.mrow >> 63) ? 0 : (row_deg(cur.mrow) + 3) >> 2;
-            const long long mat = row_first4(cur.mrow);
-            const int incl = warp_incl_scan(mn4, lane);
-            const int excl = incl - mn4;
-            const int total = __shfl_sync(kFull, incl, 31);
-            for (int i0 = 0; i0 < total; i0 += 64) {
-                int4 v[2];
-                bool ok[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int i = i0 + 32 * h + lane;
-                    ok[h] = i < total;
-                    const int ii = ok[h] ? i : total - 1;
-                    const int j = seg_search(incl, ii);
-                    const int off = ii - __shfl_sync(kFull, excl, j);
-                    const long long at = __shfl_sync(kFull, mat, j) + off;
-                    v[h] = ok[h] ? ldg_stream(adj4 + at) : sent4;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    if (i0 + 32 * h < total)
-                        light_expand4<SLOTS>(ls.table, ls.list, v[h], ok[h], x, a.n_side, hbm, list_n,
-                                             lane);
-            }
-        }
-        __syncwarp();
-        // x itself was never inserted; it is in N(h), and so is nothing else of the list
-        const int hop2 = list_n + (hbm ? hub_deg - 1 : 0);
-        light_stage_b(a, nxt);
-        // ---- the pairs of the group, 32 at a time: lane l owns pair tb + l
-        for (long long tb = p0; tb < p1; tb += 32) {
-            const int count = (int)min(32ll, p1 - tb);
-            unsigned long long row = 0ull;
-            int idx = 0, py = -1;
-            if (lane < count) {
-                const int2 iy = tb == p0 ? iy0 : pair_at(a, tb + lane);
-                row = a.m_row[iy.y];
-                idx = iy.x;
-                py = iy.y;
-            }
-            if (tb == p0) light_stage_c(a, nxt);
-            const int pdeg = row_deg(row);
-            const bool by_probe = lane < count && a.node_wt != nullptr && row_slot1(row) > 0 &&
-                                  (long long)a.probe_ratio * list_n <= pdeg;
-            ls.cn[lane] = 0;
-            ls.aa_lo[lane] = 0u;
-            ls.aa_hi[lane] = 0u;
-            __syncwarp();
-            unsigned my_cn = 0;
-            unsigned long long my_aa = 0ull;
-            // partners with a bitmap: the hop-2 list against the bitmap
-            unsigned todo = __ballot_sync(kFull, by_probe);
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const unsigned long long r = __shfl_sync(kFull, row, j);
-                const unsigned* hb = a.hub_bm + (size_t)(row_slot1(r) - 1) * (size_t)a.hub_words;
-                unsigned cnt = 0;
-                unsigned long long acc = 0ull;
-                if (hbm && lane == 0) {
-                    // the hub's share |N(h) & N(y)| from the table, minus x when x is in N(y)
-                    const int t = hub_tab + row_slot1(r) - 1;
-                    cnt = (unsigned)a.hubtab_cn[t];
-                    acc = a.hubtab_aa[t];
-                }
-                if (hbm) {
-                    const int yj = __shfl_sync(kFull, py, j);
-                    const bool x_in = __any_sync(kFull, cur.m == yj);   // y in N(x)
-                    if (x_in && lane == 0) {
-                        cnt -= 1u;
-                        acc -= (unsigned long long)__ldg(a.node_wt + x);
-                    }
-                }
-                for (int i0 = lane; i0 < list_n; i0 += 128) {
-                    int w[4];
-                    unsigned word[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)   // bit n_side is never on in a hub bitmap
-                        w[k] = i0 + 32 * k < list_n ? ls.list[i0 + 32 * k] : a.n_side;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) word[k] = __ldg(hb + (w[k] >> 5));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if ((word[k] >> (w[k] & 31)) & 1u) {
-                            ++cnt;
-                            acc += __ldg(a.node_wt + w[k]);
-                        }
-                }
-                cnt = __reduce_add_sync(kFull, cnt);
-                if (cnt > 0) acc = light_sum64(acc);
-                if (lane == j) {
-                    my_cn = cnt;
-                    my_aa = cnt > 0 ? acc : 0ull;
-                }
-            }
-            // every other partner list, flattened: streamed against the table (and the hub's bitmap)
-            if (hop2 > 0) {
-                const int pn4 = (lane < count && !by_probe) ? (pdeg + 3) >> 2 : 0;
-                const long long pat = row_first4(row);
-                const int incl = warp_incl_scan(pn4, lane);
-                const int excl = incl - pn4;
-                const int total = __shfl_sync(kFull, incl, 31);
-                int run_own = 0;
-                unsigned run_cnt = 0;
-                unsigned long long run_acc = 0ull;
-                for (int i0 = 0; i0 < total; i0 += 64) {
-                    int4 v[2];
-                    uint4 wt[2];
-                    int own[2];
-                    bool ok[2];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int i = i0 + 32 * h + lane;
-                        ok[h] = i < total;
-                        const int ii = ok[h] ? i : total - 1;
-                        own[h] = seg_search(incl, ii);
-                        const int off = ii - __shfl_sync(kFull, excl, own[h]);
-                        const long long at = __shfl_sync(kFull, pat, own[h]) + off;
-                        v[h] = ok[h] ? ldg_stream(adj4 + at) : sent4;
-                        wt[h] = ok[h] ? ldg_stream_u(adjw4 + at) : make_uint4(0u, 0u, 0u, 0u);
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (ok[h]) {
-                            // a lane meets the 128-bit words of one pair back to back: it keeps
-                            // their sum in registers and adds it to the pair's totals once
-                            if (own[h] != run_own) {
-                                if (run_cnt > 0) {
-                                    atomicAdd(&ls.cn[run_own], (int)run_cnt);
-                                    atomicAdd(&ls.aa_lo[run_own], (unsigned)(run_acc & 0xffffffull));
-                                    atomicAdd(&ls.aa_hi[run_own], (unsigned)(run_acc >> 24));
-                                }
-                                run_own = own[h];
-                                run_cnt = 0;
-                                run_acc = 0ull;
-                            }
-                            light_test4<SLOTS>(ls.table, v[h], wt[h], x, hbm, run_cnt, run_acc);
-                        }
-                    }
-                }
-                if (run_cnt > 0) {
-                    atomicAdd(&ls.cn[run_own], (int)run_cnt);
-                    atomicAdd(&ls.aa_lo[run_own], (unsigned)(run_acc & 0xffffffull));
-                    atomicAdd(&ls.aa_hi[run_own], (unsigned)(run_acc >> 24));
-                }
-                __syncwarp();
-                if (!by_probe) {
-                    my_cn = (unsigned)ls.cn[lane];
-                    my_aa = ((unsigned long long)ls.aa_hi[lane] << 24) + ls.aa_lo[lane];
-                }
-            }
-            if (tb == p0) light_stage_d(a, nxt, lane);
-            // epilogue: same expressions as k_score_side
-            if (lane < count) {
-                const int cnn = (int)my_cn;
-                const int u = hop2 + pdeg - cnn;   // |a| + |b| - |a & b|  (similarity.py:110)
-                const double jv = __ddiv_rn((double)cnn, (double)u);
-                const double av = (double)my_aa * (1.0 / (double)(1ull << BLP_AA_FRAC_BITS));
-                if (REC) {
-                    unsigned long long* rr = a.rec + 3 * (tb + lane);
-                    rr[0] = (unsigned long long)(unsigned)cnn | ((unsigned long long)(unsigned)u << 32);
-                    rr[1] = (unsigned long long)__double_as_longlong(jv);
-                    rr[2] = (unsigned long long)__double_as_longlong(av);
-                } else {
-                    if (a.cn) a.cn[idx] = cnn;
-                    if (a.uni) a.uni[idx] = u;
-                    if (a.jac) a.jac[idx] = jv;
-                    if (a.aa) a.aa[idx] = av;
-                }
-                if (a.pa) a.pa[idx] = (long long)xdeg * (long long)pdeg;
-                if (a.hop2) a.hop2[idx] = hop2;
-            }
-            __syncwarp();
-        }
-        if (p0 >= p1) {   // (never: an item has at least one pair)
-            light_stage_c(a, nxt);
-            light_stage_d(a, nxt, lane);
-        }
-        // leave the table empty for the next group
-        if (list_n > 0) {
-            int4* t4 = reinterpret_cast<int4*>(ls.table);
-            for (int i = lane; i < SLOTS / 4; i += 32) t4[i] = empty4;
-        }
-        __syncwarp();
-        light_stage_e(a, nxt);
-        cur = nxt;
-        c = c1;
-        c1 = __shfl_sync(kFull, c2, 0);
-    }
-}
-
-// Per node of the grouping side: can its group go to k_score_light?  (run once per graph)
-// Yes when it has <= 32 middle nodes, at most one of them an OR-hub (and only if the hub tables
-// exist), and the other lists together hold <= kLightCap ids.
-__global__ void k_flag_light(int n_side, const unsigned long long* __restrict__ g_row,
-                             const int* __restrict__ g_adj,
-                             const unsigned long long* __restrict__ m_xrow, int max_hubs,
-                             unsigned char* __restrict__ light) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n_side) return;
-    const unsigned long long xr = g_row[x];
-    const int d = row_deg(xr);
-    bool ok = d >= 1 && d <= 32;
-    long long walked = 0;
-    int hubs = 0;
-    if (ok) {
-        const int* adj = g_adj + row_first4(xr) * 4;
-        for (int i = 0; i < d; ++i) {
-            const unsigned long long r = m_xrow[adj[i]];
-            if (r >> 63) ++hubs;
-            else walked += row_deg(r);
-        }
-    }
-    light[x] = (ok && hubs <= max_hubs && walked <= kLightCap) ? 1 : 0;
-}
-
-// One CTA per (bitmap node y, OR-hub h): |N(h) & N(y)| and the Q1.31 weight sum over it.
-__global__ void k_hub_tables(const int* __restrict__ or_nodes, int n_bm,
-                             const unsigned long long* __restrict__ m_row,
-                             const int* __restrict__ m_adj, const unsigned* __restrict__ hub_bm,
-                             int bm_words, const unsigned* __restrict__ node_wt,
-                             int* __restrict__ tab_cn, unsigned long long* __restrict__ tab_aa) {
-    const int y = blockIdx.x, o = blockIdx.y;
-    const unsigned long long row = m_row[or_nodes[o]];
-    const int* adj = m_adj + row_first4(row) * 4;
-    const unsigned* bm = hub_bm + (size_t)y * bm_words;
-    const int padded = ((row_deg(row) + 3) >> 2) << 2;   // rows are bank-striped: padding is interleaved
-    unsigned cnt = 0;
-    unsigned long long acc = 0ull;
-    for (int i = threadIdx.x; i < padded; i += blockDim.x) {
-        const int id = adj[i];   // the padding id's bit is never on
-        if ((bm[id >> 5] >> (id & 31)) & 1u) {
-            ++cnt;
-            acc += node_wt[id];
-        }
-    }
-    __shared__ unsigned s_cnt;
-    __shared__ unsigned long long s_acc;
-    if (threadIdx.x == 0) {
-        s_cnt = 0;
-        s_acc = 0ull;
-    }
-    __syncthreads();
-    cnt = __reduce_add_sync(kFull, cnt);
-    if (cnt > 0) {
-        acc = light_sum64(acc);
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&s_cnt, cnt);
-            atomicAdd(&s_acc, acc);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        tab_cn[(size_t)o * n_bm + y] = (int)s_cnt;
-        tab_aa[(size_t)o * n_bm + y] = s_acc;
-    }
-}
-
-// Items -> two lists of item indices (warp-per-group kernel / CTA kernel), any order.
-enum { SC_N_ITEMS = 0, SC_HEAVY_WORK = 1, SC_N_RUNS = 2, SC_MODE = 3, SC_N_LIGHT = 4, SC_N_HEAVY = 5,
-       SC_LIGHT_WORK = 6, SC_COUNT = 8 };
-__global__ void k_split_items(int* __restrict__ scalars, const int* __restrict__ item_key,
-                              const unsigned char* __restrict__ light, int n_side,
-                              int* __restrict__ light_list, int* __restrict__ heavy_list) {
-    const int n = scalars[SC_N_ITEMS];
-    const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
-    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += stride) {
-        const int i = base + lane;
-        int cls = -1;   // 0 CTA kernel, 1 warp-per-group kernel
-        if (i < n) {
-            const int key = item_key[i];
-            cls = key < n_side ? light[key] : 0;
-        }
-        const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const unsigned m = __ballot_sync(kFull, cls == k);
-            int b = 0;
-            if (lane == 0 && m) b = atomicAdd(&scalars[k == 0 ? SC_N_HEAVY : SC_N_LIGHT], __popc(m));
-            b = __shfl_sync(kFull, b, 0);
-            int* dst = k == 0 ? heavy_list : light_list;
-            if (cls == k) dst[b + __popc(m & lt)] = i;
-        }
-    }
-}
-
-template <int CAP, int SLOTS, int WARPS, bool REC>
-static int launch_light(blp_graph* g, const SideArgs& a, int use_sms, cudaStream_t st) {
-    const size_t smem = sizeof(LightSmem<CAP, SLOTS>) * WARPS;
-    int& per_sm = g->light_ctas_per_sm[REC ? 1 : 0];
-    if (per_sm == 0) {
-        BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_light<CAP, SLOTS, WARPS, REC>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        BLP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &occ, k_score_light<CAP, SLOTS, WARPS, REC>, WARPS * 32, smem));
-        if (occ < 1) {
-            set_error("blp_score_pairs: the warp-per-group kernel does not fit on an SM");
-            return BLP_ERR_UNSUPPORTED;
-        }
-        per_sm = occ;
-    }
-    k_score_light<CAP, SLOTS, WARPS, REC><<<per_sm * use_sms, WARPS * 32, smem, st>>>(a);
-    BLP_CUDA_TRY(cudaGetLastError());
-    return BLP_OK;
-}
 
 template <int NT, bool RANGED, bool REC>
 static int launch_side(const SideArgs& a, int grid, size_t smem, cudaStream_t st) {
@@ -2040,6 +1169,9 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         ++launches;
     }
     if (rc == BLP_OK) {
+        // work-item counts of this call, for blp_score_stats (the scalars live in scratch)
+        cudaMemcpyAsync(g->d_counts[side], scalars + SC_N_ITEMS, sizeof(int), cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(g->d_counts[side] + 1, scalars + SC_N_LIGHT, sizeof(int), cudaMemcpyDeviceToDevice, st);
         if (cudaEventRecord(g->ev[side][2], st) == cudaSuccess) g->ev_recorded[side] = true;
         stats.ctas = per_sm * use_sms;
         stats.threads_per_cta = nt;

@@ -16,7 +16,10 @@
  *     reference's shared id space onto them).  In a pair, an index that is negative, out of range
  *     or names a node of degree 0 means "id not in graph": every output of that pair is 0
  *     (similarity.py:59-60, 104-105).
- *   - A handle is immutable after creation; scoring calls on distinct streams are re-entrant.
+ *   - A handle's graph is immutable after creation.  Scoring calls issued by ONE host thread on
+ *     several streams overlap on the device; concurrent calls from several host threads on the
+ *     same handle are not supported (the handle owns a side stream, events and the accounting
+ *     of the last call) -- use one handle per thread.
  *   - There is no CPU fallback: without a CUDA device every compute entry point fails with
  *     BLP_ERR_CUDA.
  */
@@ -68,7 +71,7 @@ typedef struct blp_graph_info_t {
 /* Per-launch accounting of the last blp_score_pairs call on a handle (for bench / roofline). */
 typedef struct blp_score_stats_t {
     int64_t n_pairs;
-    int64_t n_groups;         /* distinct hop-2 sets built */
+    int64_t n_groups;         /* work items = distinct hop-2 sets built (+1 for the "not in graph" bucket) */
     int32_t kernel_launches;  /* kernels launched by the call */
     int32_t ctas;             /* grid of the scoring kernel */
     int32_t threads_per_cta;
@@ -76,7 +79,8 @@ typedef struct blp_score_stats_t {
     int32_t range_passes;     /* id-range passes over the hop-2 bitmap (1 = fits shared memory) */
     float group_ms;           /* CUDA-event time of the grouping kernels (count, scan, scatter) */
     float score_ms;           /* CUDA-event time of the scoring kernels alone, on their own stream */
-    float light_ms;           /* ... of which the warp-per-group kernel (light groups), 0 if not used */
+    float light_ms;           /* span of the warp-per-group kernel (it runs beside the CTA kernel), 0 if not used */
+    int32_t light_groups;     /* work items scored by the warp-per-group kernel */
 } blp_score_stats_t;
 
 int blp_version(void);
@@ -187,7 +191,8 @@ int blp_eval_roc_auc(const int32_t* labels, const double* scores, int64_t n,
  */
 int blp_graph_reserve_sms(blp_graph* g, int n_sms);
 
-/* Accounting of the most recent blp_score_pairs on this handle (per side).  The two event times
+/* Accounting of the most recent blp_score_pairs on this handle (per side; with
+ * blp_score_pairs_host: of the last slice).  The two event times
  * are valid once that call's work has completed (the function waits for its end event). */
 int blp_score_stats(const blp_graph* g, int side, blp_score_stats_t* stats);
 
