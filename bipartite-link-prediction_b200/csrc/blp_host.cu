@@ -90,11 +90,12 @@ extern "C" int blp_score_pairs_host(blp_graph* g, const int32_t* pair_u, const i
         set_error("blp_score_pairs_host: bad argument");
         return BLP_ERR_INVALID;
     }
-    for (void* p : h_out)
-        if (n > 0 && !p) {
-            set_error("blp_score_pairs_host: every output column is required");
-            return BLP_ERR_INVALID;
-        }
+    bool any = false;
+    for (void* p : h_out) any = any || p != nullptr;
+    if (n > 0 && !any) {
+        set_error("blp_score_pairs_host: no output column given");
+        return BLP_ERR_INVALID;
+    }
     if (n == 0) return BLP_OK;
     BLP_CUDA_TRY(cudaSetDevice(g->device));
     int rc = host_state_reserve(g, n);
@@ -174,7 +175,8 @@ extern "C" int blp_score_pairs_host(blp_graph* g, const int32_t* pair_u, const i
         if (err == cudaSuccess) err = cudaEventRecord(ev, from);
         if (err == cudaSuccess) err = cudaStreamWaitEvent(h->copy, ev, 0);
         for (int k = first; k <= last && err == cudaSuccess; ++k)
-            err = cudaMemcpyAsync((char*)h_out[k] + (size_t)kElem[k] * (size_t)lo,
+            if (h_out[k])   // a null column is computed but not copied back
+                err = cudaMemcpyAsync((char*)h_out[k] + (size_t)kElem[k] * (size_t)lo,
                                   (char*)h->d_out[k] + (size_t)kElem[k] * (size_t)lo,
                                   (size_t)kElem[k] * (size_t)(hi - lo), cudaMemcpyDeviceToHost, h->copy);
         return err;
@@ -189,7 +191,7 @@ extern "C" int blp_score_pairs_host(blp_graph* g, const int32_t* pair_u, const i
                                 (int64_t*)at(8, lo), nullptr, st);
         if (r != BLP_OK) return r;
         cudaError_t e = copy_back(st, 0, 3, lo, hi);
-        if (e == cudaSuccess) {   // pa travels with the user side (it is written by that kernel)
+        if (e == cudaSuccess && h_out[8]) {   // pa travels with the user side (written by that kernel)
             e = cudaMemcpyAsync((char*)h_out[8] + 8 * (size_t)lo, (char*)h->d_out[8] + 8 * (size_t)lo,
                                 8 * (size_t)(hi - lo), cudaMemcpyDeviceToHost, h->copy);
         }

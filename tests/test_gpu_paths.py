@@ -157,9 +157,15 @@ def test_host_buffer_entry_point(mods):
     assert rc == lib_mod.BLP_OK
     for k, c in zip(sess.KEYS, cols):
         assert np.array_equal(c, want[k]), k
-    # argument checking: a missing output column is refused, n = 0 is a no-op
-    bad = [c.ctypes.data for c in cols]
-    bad[3] = None
-    assert G._lib.blp_score_pairs_host(G._h, pu_c.ctypes.data, pv_c.ctypes.data, n, *bad, 0, -1, 0) \
-        == lib_mod.BLP_ERR_INVALID
+    # a NULL column is skipped (not copied back); no column at all is refused; n = 0 is a no-op
+    some = [c.ctypes.data for c in cols]
+    cols[3][:] = -7.0
+    some[3] = None
+    some[5] = None
+    cols[0][:] = 0
+    assert G._lib.blp_score_pairs_host(G._h, pu_c.ctypes.data, pv_c.ctypes.data, n, *some, 2, 1, 1) \
+        == lib_mod.BLP_OK
+    assert np.array_equal(cols[0], want['u_cn']) and np.all(cols[3] == -7.0)
+    assert G._lib.blp_score_pairs_host(G._h, pu_c.ctypes.data, pv_c.ctypes.data, n, *([None] * 9),
+                                       0, -1, 0) == lib_mod.BLP_ERR_INVALID
     assert G._lib.blp_score_pairs_host(G._h, None, None, 0, *([None] * 9), 0, -1, 0) == lib_mod.BLP_OK
