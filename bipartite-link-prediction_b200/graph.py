@@ -356,11 +356,10 @@ class BipartiteGraph(object):
 
 
 class HostSession(object):
-    """End-to-end scoring with HOST buffers: pinned staging, H2D of the pair ids, both sides on
-    the device, D2H of all outputs (56 B per pair), overlapped on two streams.
-
-    The business side runs first; the user side (the long one) then overlaps with the D2H of the
-    business-side results, and only the user-side copy-back is exposed at the end.
+    """End-to-end scoring with HOST buffers: page-locked pair and result arrays owned by the
+    session, and ONE C-ABI call per step (`blp_score_pairs_host`) that uploads the ids, scores
+    both sides and copies the nine columns (56 B per pair) back, the copies overlapping the
+    kernels inside the library.  `score_pinned_py` drives the same pipeline from Python.
     """
 
     KEYS = ('u_cn', 'u_union', 'u_jaccard', 'u_adamic', 'b_cn', 'b_union', 'b_jaccard',
