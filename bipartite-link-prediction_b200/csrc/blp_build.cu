@@ -540,7 +540,8 @@ extern "C" int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n
         g->n_biz_in += d > 0;
         g->max_bdeg = std::max(g->max_bdeg, d);
     }
-    if (u_len / 4 >= (1ull << 40) || b_len / 4 >= (1ull << 40) || g->max_udeg >= (1 << 24) ||
+    if (u_len / 4 >= (1ull << BLP_ROW_FIRST4_BITS) || b_len / 4 >= (1ull << BLP_ROW_FIRST4_BITS) ||
+        g->max_udeg >= (1 << 24) ||
         g->max_bdeg >= (1 << 24)) {
         set_error("blp_graph_create_device: graph too large for the packed row descriptors");
         return fail(BLP_ERR_UNSUPPORTED);

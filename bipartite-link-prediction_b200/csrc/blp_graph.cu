@@ -283,7 +283,9 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
             g->max_bdeg = std::max(g->max_bdeg, d);
         }
         // packed row descriptors
-        if (u_off[n_users] / 4 >= (1LL << 40) || b_off[n_biz] / 4 >= (1LL << 40) ||
+        // (first entry / 4) has BLP_ROW_FIRST4_BITS bits in the descriptor: 2^30 padded entries
+        if (u_off[n_users] / 4 >= (1LL << BLP_ROW_FIRST4_BITS) ||
+            b_off[n_biz] / 4 >= (1LL << BLP_ROW_FIRST4_BITS) ||
             g->max_udeg >= (1 << 24) || g->max_bdeg >= (1 << 24)) {
             delete g;
             blp::set_error("blp_graph_create: graph too large for the packed row descriptors");

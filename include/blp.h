@@ -94,6 +94,9 @@ int blp_device_count(int* count);
  * CSR directions, degree tables and the Adamic-Adar weight table 1/ln(deg) (similarity.py:121-123)
  * are made resident in HBM.  edge_u / edge_b are HOST arrays of n_edges local indices
  * (column 0 = user, column 1 = business of graph.txt, dataset_maker.py:197).
+ * Limits of the packed row descriptors: degrees below 2^24 and at most 2^30 adjacency entries per
+ * direction after padding every row to a multiple of four (about a billion distinct edges);
+ * beyond that the call fails with BLP_ERR_UNSUPPORTED.
  */
 int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
                      const int32_t* edge_u, const int32_t* edge_b,
