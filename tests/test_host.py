@@ -39,6 +39,9 @@ def test_argument_validation_precedes_device_use(built_lib):
     assert built_lib.blp_graph_create(4, 3, 2, None, None, 0, ctypes.byref(h)) == lib_mod.BLP_ERR_INVALID
     assert built_lib.blp_graph_destroy(None) == lib_mod.BLP_OK
     assert built_lib.blp_score_pairs(None, 0, None, None, 0, *([None] * 7)) == lib_mod.BLP_ERR_INVALID
+    assert built_lib.blp_score_pairs_host(None, None, None, 0, *([None] * 9), 0, -1, 0) \
+        == lib_mod.BLP_ERR_INVALID
+    assert b'blp_score_pairs_host' in built_lib.blp_last_error()
     with pytest.raises(ValueError):
         lib_mod.check(lib_mod.BLP_ERR_INVALID, 'x')
     with pytest.raises(RuntimeError):
