@@ -4,13 +4,17 @@
 // x (users() loop A, similarity.py:24-33 / business() loop A', :67-78), then for every candidate
 // pair (x, y) intersect hop2(x) with N(y) (loops C / C', :48-61 / :91-106) and derive
 // common_neighbors, jaccard and adamic_adar (:108-126).  Both sides are the same computation
-// with the two CSR directions swapped, so there is one kernel:
+// with the two CSR directions swapped, so one set of kernels serves both:
 //
-//   hop2(x) = ( U_{m in N(x)} N(m) ) \ {x}        held as a bitmap in shared memory
-//   cn(x,y) = | { i in N(y) : bit i set } |        N(y) streamed with 128-bit loads
+//   hop2(x) = ( U_{m in N(x)} N(m) ) \ {x}        held in shared memory: a bitmap over the whole
+//                                                 universe (k_score_side, one CTA per group) or a
+//                                                 hash table + id list (k_score_light, one warp)
+//   cn(x,y) = | { i in N(y) : i in hop2(x) } |     N(y) streamed with 128-bit loads -- or, when y
+//                                                 has a bitmap of its own, hop2(x) probed into it
 //
-// Work distribution.  Pairs are grouped by x with a counting sort (k_group_*).  A persistent grid
-// pulls groups from an atomic counter.  Inside a CTA both the expansion and the intersection
+// Work distribution.  Pairs are grouped by x (runs of an already grouped list, or a counting sort:
+// k_group_*), the groups are split by size class, and two persistent grids pull their groups from
+// atomic counters.  Inside a CTA of k_score_side both the expansion and the intersection
 // phase walk a *set of adjacency lists* whose lengths span 1 .. >100k: the lists of a tile are
 // cut into 512-id chunks, the chunk counts are prefix-summed in shared memory and warps take
 // chunks round-robin, so a hub list is spread over the whole CTA while short lists cost one
