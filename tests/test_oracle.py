@@ -135,3 +135,51 @@ def test_three_oracles_agree_on_random_graphs(g):
     assert np.all(cn >= 0) and np.all(uni >= 1) and np.all(cn <= uni)
     aa = np.asarray(a['u_adamic'], dtype=np.float64)[ok]
     assert np.all(aa <= cn / np.log(2.0) + 1e-12)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.integers(0, 10_000))
+def test_set_identities_behind_the_probe_and_table_paths(seed):
+    """The CUDA path answers some pairs without streaming N(y).  The identities it relies on,
+    checked on the reference's own set semantics (Oracle A):
+
+      probe path   cn(x,y) = |{w in hop2(x) : w in N(y)}|        (iterate the small side)
+      one-hub path hop2(x) = (N(h) \\ {x})  +  S'   disjoint, S' = U_{m in N(x), m != h} N(m) \\ N(h) \\ {x}
+                   |hop2(x)| = deg(h) - 1 + |S'|
+                   cn(x,y)   = |S' & N(y)| + |N(h) & N(y)| - [x in N(y)]
+                   aa(x,y)   likewise with weights, minus w(x) when x in N(y)
+    for every middle node h of x (the kernel uses the one that is a hub)."""
+    import math
+    rng = np.random.default_rng(seed)
+    n_users, n_biz, m = 40, 12, 140
+    eu = rng.integers(0, n_users, m)
+    eb = rng.integers(0, n_biz, m) + 1000            # shared id space, disjoint columns
+    G = oa.MiniSnapGraph.from_edges(zip(eu.tolist(), eb.tolist()))
+
+    def w(i):
+        d = G.degree(i)
+        return 1.0 / math.log(d) if d > 1 else 0.0
+
+    users = sorted(set(eu.tolist()))
+    for x in users[:12]:
+        hop2 = set(G.nodes_at_hop(x, 2))
+        mids = sorted(G.nodes_at_hop(x, 1))
+        for y in sorted(set(eb.tolist()))[:6]:
+            ny = set(G.nodes_at_hop(y, 1))
+            cn = oa.common_neighbors(hop2, ny)
+            assert cn == sum(1 for i in hop2 if i in ny)                       # probe path
+            for h in mids:
+                nh = set(G.nodes_at_hop(h, 1))
+                s_prime = set()
+                for mnode in mids:
+                    if mnode != h:
+                        s_prime |= set(G.nodes_at_hop(mnode, 1))
+                s_prime -= nh
+                s_prime.discard(x)
+                assert hop2 == (nh - {x}) | s_prime and not ((nh - {x}) & s_prime)
+                assert len(hop2) == G.degree(h) - 1 + len(s_prime)
+                x_in = 1 if x in ny else 0
+                assert cn == len(s_prime & ny) + len(nh & ny) - x_in
+                aa = oa.adamic_adar(hop2, ny, G)
+                alt = (sum(w(i) for i in s_prime & ny) + sum(w(i) for i in nh & ny) - x_in * w(x))
+                assert aa == pytest.approx(alt, rel=1e-12, abs=1e-12)
