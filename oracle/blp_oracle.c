@@ -1,7 +1,7 @@
 /*
  * blp_oracle.c -- plain-C CPU restatement of the reference's similarity.py
- * (TEST INFRASTRUCTURE ONLY; PARITY UNPINNED: the reference ships no golden vectors and cannot
- * run here, see similarity_oracle.py).  A third, independent statement of the same algorithm,
+ * (TEST INFRASTRUCTURE ONLY; pinned to the reference's own code through Oracle A and the fixtures
+ * that code wrote, see similarity_oracle.py / ref_runner.py).  A third, independent statement of the same algorithm,
  * fast enough to check the CUDA path at the full BASELINE.json sizes.  Only tests/,
  * __graft_entry__.smoke() and bench.py's CPU-baseline legs may load it; the product never does.
  *

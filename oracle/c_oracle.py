@@ -1,4 +1,4 @@
-"""ctypes loader for oracle/blp_oracle.c (TEST INFRASTRUCTURE ONLY; parity unpinned)."""
+"""ctypes loader for oracle/blp_oracle.c (TEST INFRASTRUCTURE ONLY; pinned to the reference through Oracle A, see similarity_oracle.py)."""
 import ctypes
 import os
 import subprocess
@@ -39,3 +39,21 @@ def score_pair_arrays(n_users, n_biz, edge_u, edge_b, pair_u, pair_b):
     if rc != 0:
         raise RuntimeError('blp_oracle_score failed: %d' % rc)
     return out
+
+
+def score_pair_arrays_parallel(n_users, n_biz, edge_u, edge_b, pair_u, pair_b, threads=None):
+    """The same over contiguous slices of the pair list on `threads` host threads (the C call
+    releases the GIL; every slice rebuilds the graph, as a separate process would)."""
+    from concurrent.futures import ThreadPoolExecutor
+    load()
+    threads = threads or len(os.sched_getaffinity(0))
+    n = len(pair_u)
+    threads = max(1, min(threads, n // 1000 or 1))
+    bounds = [(n * t) // threads for t in range(threads + 1)]
+    pu = np.ascontiguousarray(pair_u, dtype=np.int32)
+    pv = np.ascontiguousarray(pair_b, dtype=np.int32)
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(lambda lh: score_pair_arrays(n_users, n_biz, edge_u, edge_b,
+                                                         pu[lh[0]:lh[1]], pv[lh[0]:lh[1]]),
+                            zip(bounds[:-1], bounds[1:])))
+    return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}

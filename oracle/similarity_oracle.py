@@ -1,11 +1,15 @@
 """Oracle A -- CPU restatement of the reference's similarity.py (TEST INFRASTRUCTURE ONLY).
 
-PARITY UNPINNED: the reference ships no tests, fixtures or golden outputs for this path
- and cannot run here (Python-2-only source, SNAP binding `_snap.so`
-stripped from the mount).  This file restates the reference's algorithm in Python 3 loop by
-loop; it is pinned only by redundancy: the hand-checked known-answer table in
-tests/golden/known_answer.json, an independent sparse-algebra oracle (algebra_oracle.py) and the
-C restatement (blp_oracle.c) all have to agree with it.
+PARITY PINNED TO THE REFERENCE'S OWN CODE: the reference ships no tests, fixtures or golden
+outputs for this path, and its source is Python-2-only with a stripped SNAP
+binding, so it cannot be imported as it lies.  oracle/build_ref.py compiles the reference's
+similarity.py / util.py from /root/reference into oracle/_ref/ (three mechanical 2->3 rewrites,
+bytecode only) and oracle/ref_runner.py executes it with a stand-in for SNAP's four calls.  This
+restatement must agree with that code on the committed fixtures it wrote
+(tests/golden/cases.json, ref_files.json), on the hand-checked table (known_answer.json) and on
+hypothesis-generated graphs (tests/test_reference_pin.py); the sparse-algebra oracle
+(algebra_oracle.py) and the C restatement (blp_oracle.c) must agree with it in turn.  What stays
+unpinned is SNAP itself (binary absent): its documented behaviour is restated below.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module.  The product package never does.

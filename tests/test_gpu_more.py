@@ -57,6 +57,33 @@ def test_file_level_drop_in_matches_oracle_files(mods, tmp_path):
                         assert x == y, (fm, u, v)
 
 
+def test_file_level_drop_in_matches_the_reference_files(mods, tmp_path):
+    """similarity.main(...) against the six files the REFERENCE's own main() wrote for the same
+    graph.txt / examples.json (tests/golden/ref_files.json, made by oracle/_ref): same key sets
+    (the in-graph b_adamic entries missing, similarity.py:102), same int-vs-float types, same values."""
+    sim, util = pkg('similarity'), pkg('util')
+    doc = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'ref_files.json')))
+    (tmp_path / 'graph.txt').write_text(doc['graph_txt'])
+    util.write_json(doc['examples'], str(tmp_path / 'examples.json'))
+    names = ['u_cn', 'u_jaccard', 'u_adamic', 'b_cn', 'b_jaccard', 'b_adamic']
+    paths = [str(tmp_path / (n + '.json')) for n in names]
+    M = ['common_neighbors', 'jaccard', 'adamic_adar']
+    sim.main(str(tmp_path / 'examples.json'), str(tmp_path / 'graph.txt'), M, paths[:3], M, paths[3:],
+             reproduce_reference_bug=True)
+    for n, p in zip(names, paths):
+        got, want = util.load_json(p), doc['score_files'][n]
+        assert got.keys() == want.keys(), n
+        for u in want:
+            assert got[u].keys() == want[u].keys(), (n, u)
+            for v in want[u]:
+                x, y = got[u][v], want[u][v]
+                assert type(x) is type(y), (n, u, v, x, y)
+                if 'adamic' in n:
+                    assert x == pytest.approx(y, rel=1e-8), (n, u, v)
+                else:
+                    assert x == y, (n, u, v)
+
+
 def test_c2_sample_vs_c_oracle(mods):
     """BASELINE.json configs[1] graph (366k x 61k, 1.5M reviews), 300k-pair sample, C oracle."""
     from oracle import c_oracle
@@ -211,6 +238,20 @@ def test_full_c2_properties(mods):
     r2 = G.score_pairs(du, dv)
     for k in r2:
         assert torch.equal(r[k], r2[k]), k
+
+
+@pytest.mark.timeout(900)
+def test_full_c2_vs_c_oracle(mods):
+    """The benchmarked workload itself -- BASELINE.json configs[1], all 10M pairs -- against the C
+    oracle on every host core: every integer column bit-exact, jaccard bit-exact, adamic 1e-8."""
+    from oracle import c_oracle
+    graph, synth = mods
+    cfg, eu, eb, pu, pv = synth.make_config('C2')
+    assert pu.size == 10_000_000
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    got = G.score_pairs_host(pu, pv)
+    want = c_oracle.score_pair_arrays_parallel(cfg['n_users'], cfg['n_biz'], eu, eb, pu, pv)
+    check_against(got, want, pu.size)
 
 
 @pytest.mark.timeout(900)

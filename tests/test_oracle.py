@@ -1,8 +1,9 @@
 """CPU tests of the oracles: known-answer table, golden fixtures, three-way agreement.
 
-The reference has no tests or golden outputs, so the oracle is pinned by
-redundancy: a line-for-line restatement (A), independent sparse algebra (B) and a plain-C
-restatement (C) must agree with each other and with the hand-checked table.
+Three statements of the reference's algorithm -- a line-for-line restatement (A), independent
+sparse algebra (B) and plain C (C) -- must agree with each other, with the hand-checked table and
+with the fixtures in tests/golden/ that the reference's OWN code wrote (tests/test_reference_pin.py
+holds the tests that run that code, oracle/_ref, directly against Oracle A).
 """
 import json
 import os
