@@ -1,21 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- candidate pairs scored per second on Yelp-shaped synthetic inputs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2|C3|C4|C5] [--impl reference]
 
-A "step" is one pass of the hot path over one batch: every pair of the workload gets all seven
-reference outputs (u_cn,u_jaccard,u_adamic,b_cn,b_jaccard,b_adamic,pa, plus both union sizes).
+A "step" is one pass of the hot path over one batch: every pair of the workload gets the seven
+reference outputs (u_cn,u_jaccard,u_adamic,b_cn,b_jaccard,b_adamic,pa; the two union sizes are
+computed as well where a buffer is given).
+
 N=1 workload: BASELINE.json configs[1] ("C2": 366k users x 61k businesses, 1.5M reviews, 10M
-candidate pairs).  N>1: weak scaling -- the adjacency is replicated, every rank scores its own
-10M-pair shard of a 10M*N pair list, no collective inside the timed region; the final NCCL
-gather of the result records is timed separately and reported under "gather".
+candidate pairs).  --config C3 / C4 / C5 select the other BASELINE.json configs (C5: one GPU's
+eighth of the 1B pairs).
+
+N>1: weak scaling through the product's multi-GPU API.  ONE pair list of N x 10M pairs (the
+concatenation of N shards, each drawn exactly like the N=1 workload) is cut with
+dist.shard_bounds into user-aligned, work-balanced slices; the adjacency is replicated; every rank
+scores its slice with the columns of rank 0's peer-mapped dist.ResultWindow as the kernels' output
+arrays, so the result rows cross NVLink from inside the scoring kernels and the timed region ends
+with every row of the whole list resident on rank 0 (`value`).  Beside it: the same scoring into
+local memory (`scoring_only`) and local scoring followed by a grouped NCCL send/recv gather
+(`nccl_gather`, the baseline the fused path is measured against).  Afterwards rank 0 compares ALL
+rows with its own unsharded call and a sample with the C oracle.
 
 One JSON line on stdout (rank 0).  `value` is device-resident throughput (CUDA events, max over
-ranks); `e2e` goes through the host-buffer API (pinned H2D of the pair ids, D2H of 56 B/pair);
-`roofline` is the user-side scoring kernel (the dominant one) against MEASURED_PEAKS.json;
-`cpu_baseline` is the reference's algorithm (oracle/similarity_oracle.py, a line-for-line
-Python 3 re-execution -- the reference's own Python-2 + `_snap.so` code cannot run) on the host
-cores over a bounded sample.  `--impl reference` prints that baseline as its own line.
+ranks); `e2e` goes through the host-buffer API (pinned H2D of the pair ids, D2H of the seven
+reference outputs, 48 B/pair); `roofline` is the user-side scoring kernel (the dominant one)
+against MEASURED_PEAKS.json; `cpu_baseline` is the reference's algorithm on the host: the headline
+figure is ONE process (the reference is single-threaded) of the line-for-line restatement with set
+membership ("fair") on a C2 subsample; the faithful list-membership form,
+the reference's own code (oracle/_ref) on C1, the vectorised oracle and the plain-C port (one
+thread / every core, the latter over ALL pairs and compared with the GPU's output) sit beside it.
+`--impl reference` prints the all-core CPU arm as its own line.
 """
 import argparse
 import importlib
@@ -24,6 +38,7 @@ import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -35,8 +50,10 @@ PKG = 'bipartite-link-prediction_b200'
 METRIC = 'candidate pairs scored/sec'
 UNIT = 'pairs/s'
 METHODS = ['common_neighbors', 'jaccard', 'adamic_adar']
-NOTE = ('reference _snap.so (Python 2) unavailable -- CPU baseline is a line-for-line '
-        "re-execution of similarity.py's formulas (oracle/similarity_oracle.py, set membership)")
+NOTE = ('reference _snap.so (Python 2) unavailable -- the CPU baseline is a line-for-line '
+        "re-execution of similarity.py's formulas (oracle/similarity_oracle.py); the reference's own "
+        'similarity.py (oracle/_ref: bytecode of the unmodified functions + a SNAP stand-in) is timed '
+        'on C1 beside it and agrees with it row for row')
 
 
 def pkg(sub):
@@ -60,20 +77,34 @@ def _cpu_worker(args):
     return time.perf_counter() - t
 
 
-def cpu_reference(cfg, eu, eb, pu, pv, n_user_groups, n_biz_groups, procs):
-    """Times the reference algorithm on structure-preserving samples of the workload.
+def _cpu_worker_packed(args):
+    side, ex = args
+    from oracle import similarity_oracle as oa
+    t = time.perf_counter()
+    oa.business(ex, _G, METHODS, [None] * 3, write=False)
+    return time.perf_counter() - t
 
-    User side: ALL pairs of the first `n_user_groups` example users (hop2(u) amortised over the
-    same K pairs as in the full run).  Business side: ALL pairs of `n_biz_groups` seeded-random
-    candidate businesses (hop2(v) amortised over as many pairs as in the full run).  The two
-    per-pair costs add: rate = 1 / (t_u/S_u + t_b/S_b).  Graph loading is not timed.
-    """
+
+def _samples(pu, pv, n_user_groups, n_biz_groups):
+    """Structure-preserving samples: ALL pairs of the first n example users (hop2(u) amortised over
+    the same K pairs as in the full run) / ALL pairs of n seeded-random candidate businesses."""
+    ok = (pu >= 0) & (pv >= 0)
+    users_sorted = np.unique(pu[ok])
+    sel_u = ok & np.isin(pu, users_sorted[:n_user_groups])
+    rng = np.random.default_rng(7)
+    bizs = np.unique(pv[ok])
+    sel_b = ok & np.isin(pv, rng.choice(bizs, size=min(n_biz_groups, bizs.size), replace=False))
+    return sel_u, sel_b
+
+
+def cpu_reference_all_cores(cfg, eu, eb, pu, pv, n_user_groups, n_biz_groups, procs):
+    """Oracle A (set membership) on every host core over structure-preserving samples; the two
+    per-pair costs add: rate = 1 / (t_u/S_u + t_b/S_b).  Graph loading is not timed."""
     global _G, _EX
     import multiprocessing as mp
     from oracle import similarity_oracle as oa
     synth = pkg('synth')
     n_users = cfg['n_users']
-    ok = (pu >= 0) & (pv >= 0)
     ids_eu, ids_eb = synth.shared_ids(n_users, eu, eb)
     _G = oa.MiniSnapGraph.from_edges(zip(ids_eu.tolist(), ids_eb.tolist()))
     ctx = mp.get_context('fork')
@@ -90,18 +121,14 @@ def cpu_reference(cfg, eu, eb, pu, pv, n_user_groups, n_biz_groups, procs):
                 for v in _EX[u]:
                     byb.setdefault(v, []).append(u)
             bl = list(byb.keys())
-            shards = []
-            for p in range(procs):
-                us = set()
-                for v in bl[p::procs]:
-                    us.update(byb[v])
-                shards.append(sorted(us))
-            # each shard only keeps its own businesses' pairs
             full = _EX
             packs = []
             for p in range(procs):
                 mine = set(bl[p::procs])
-                packs.append({u: {v: 0 for v in full[u] if v in mine} for u in shards[p]})
+                us = set()
+                for v in mine:
+                    us.update(byb[v])
+                packs.append({u: {v: 0 for v in full[u] if v in mine} for u in sorted(us)})
             t0 = time.perf_counter()
             with ctx.Pool(procs) as pool:
                 pool.map(_cpu_worker_packed, [('b', pk) for pk in packs])
@@ -112,11 +139,7 @@ def cpu_reference(cfg, eu, eb, pu, pv, n_user_groups, n_biz_groups, procs):
             pool.map(_cpu_worker, [(side, sh) for sh in shards])
         return time.perf_counter() - t0, int(sel.sum())
 
-    users_sorted = np.unique(pu[ok])
-    sel_u = ok & np.isin(pu, users_sorted[:n_user_groups])
-    rng = np.random.default_rng(7)
-    bizs = np.unique(pv[ok])
-    sel_b = ok & np.isin(pv, rng.choice(bizs, size=min(n_biz_groups, bizs.size), replace=False))
+    sel_u, sel_b = _samples(pu, pv, n_user_groups, n_biz_groups)
     t_u, s_u = run('u', sel_u)
     t_b, s_b = run('b', sel_b)
     rate = 1.0 / (t_u / s_u + t_b / s_b)
@@ -126,48 +149,132 @@ def cpu_reference(cfg, eu, eb, pu, pv, n_user_groups, n_biz_groups, procs):
               (s_u, n_user_groups, t_u, s_b, n_biz_groups, t_b, procs))
     _G = None
     _EX = None
-    sides = {'user_pairs_per_s': s_u / t_u, 'business_pairs_per_s': s_b / t_b}
-    # for context: the plain-C restatement (oracle/blp_oracle.c), one thread, first 1M pairs
-    try:
-        from oracle import c_oracle
-        m = min(int(pu.size), 1_000_000)
-        t0 = time.perf_counter()
-        c_oracle.score_pair_arrays(cfg['n_users'], cfg['n_biz'], eu, eb, pu[:m], pv[:m])
-        sides['c_port_1thread_pairs_per_s'] = m / (time.perf_counter() - t0)
-        sides['c_port_sample'] = 'first %d pairs, graph build included' % m
-        # ... and on every core: `procs` processes, each a contiguous slice of the whole list
-        global _CP
-        _CP = (cfg['n_users'], cfg['n_biz'], eu, eb, pu, pv)
-        bounds = [(int(pu.size) * p) // procs for p in range(procs + 1)]
-        t0 = time.perf_counter()
-        with ctx.Pool(procs) as pool:
-            pool.map(_c_port_worker, list(zip(bounds[:-1], bounds[1:])))
-        sides['c_port_all_cores_pairs_per_s'] = int(pu.size) / (time.perf_counter() - t0)
-        sides['c_port_all_cores_sample'] = ('all %d pairs in %d contiguous slices, one process each, '
-                                            'graph build included in every process' % (pu.size, procs))
-        _CP = None
-    except Exception as exc:   # the C oracle is optional context, never the headline
-        sides['c_port_error'] = repr(exc)
-    return rate, sample, sides
+    return rate, sample, {'user_pairs_per_s': s_u / t_u, 'business_pairs_per_s': s_b / t_b}
 
 
-_CP = None
-
-
-def _c_port_worker(lohi):
-    from oracle import c_oracle
-    n_users, n_biz, eu, eb, pu, pv = _CP
-    lo, hi = lohi
-    c_oracle.score_pair_arrays(n_users, n_biz, eu, eb, pu[lo:hi], pv[lo:hi])
-    return hi - lo
-
-
-def _cpu_worker_packed(args):
-    side, ex = args
+def cpu_single_process(cfg, eu, eb, pu, pv, n_user_groups, n_biz_groups):
+    """BASELINE.md section 2, the figure the >=100x target is judged against: ONE process of the
+    line-for-line restatement with set membership ("fair") on a subsample of this workload."""
     from oracle import similarity_oracle as oa
-    t = time.perf_counter()
-    oa.business(ex, _G, METHODS, [None] * 3, write=False)
-    return time.perf_counter() - t
+    synth = pkg('synth')
+    n_users = cfg['n_users']
+    ids_eu, ids_eb = synth.shared_ids(n_users, eu, eb)
+    G = oa.MiniSnapGraph.from_edges(zip(ids_eu.tolist(), ids_eb.tolist()))
+    sel_u, sel_b = _samples(pu, pv, n_user_groups, n_biz_groups)
+    out = []
+    for side, sel in (('u', sel_u), ('b', sel_b)):
+        ids_pu, ids_pv = synth.shared_ids(n_users, pu[sel], pv[sel])
+        ex = synth.examples_dict(ids_pu, ids_pv)
+        t0 = time.perf_counter()
+        (oa.users if side == 'u' else oa.business)(ex, G, METHODS, [None] * 3, write=False)
+        out.append((time.perf_counter() - t0, int(sel.sum())))
+    (t_u, s_u), (t_b, s_b) = out
+    rate = 1.0 / (t_u / s_u + t_b / s_b)
+    sample = ('ONE process, set membership; user side: all %d pairs of the first %d example users in '
+              '%.1fs; business side: all %d pairs of %d seeded-random candidate businesses in %.1fs; '
+              'combined as 1/(t_u/S_u+t_b/S_b); graph load untimed' %
+              (s_u, n_user_groups, t_u, s_b, n_biz_groups, t_b))
+    return rate, sample, {'user_pairs_per_s': s_u / t_u, 'business_pairs_per_s': s_b / t_b}
+
+
+def cpu_c1_legs(n_example_users=300):
+    """BASELINE.json configs[0] (the reference's own CPU-runnable case), one process: the faithful
+    form (node ids in a LIST, similarity.py:22,52), the fair form, the reference's OWN code
+    (oracle/_ref) and the vectorised oracle."""
+    from oracle import algebra_oracle as ob
+    from oracle import ref_runner as rr
+    from oracle import similarity_oracle as oa
+    synth = pkg('synth')
+    cfg, eu, eb, pu, pv = synth.make_config('C1')
+    ids_eu, ids_eb = synth.shared_ids(cfg['n_users'], eu, eb)
+    G = oa.MiniSnapGraph.from_edges(zip(ids_eu.tolist(), ids_eb.tolist()))
+    ok = (pu >= 0) & (pv >= 0)
+    sel = ok & np.isin(pu, np.unique(pu[ok])[:n_example_users])
+    ids_pu, ids_pv = synth.shared_ids(cfg['n_users'], pu[sel], pv[sel])
+    ex = synth.examples_dict(ids_pu, ids_pv)
+    s = int(sel.sum())
+    legs = {'c1_sample': 'all %d pairs of the first %d example users of C1 (10k x 2k, 50k review '
+                         'lines), both sides, three methods each, one process' % (s, n_example_users)}
+    res = {}
+    for name, faithful in (('fair', False), ('faithful', True)):
+        t0 = time.perf_counter()
+        ru = oa.users(ex, G, METHODS, [None] * 3, write=False, faithful=faithful)
+        rb = oa.business(ex, G, METHODS, [None] * 3, write=False, faithful=faithful,
+                         reproduce_reference_bug=True)
+        legs['c1_%s_pairs_per_s' % name] = s / (time.perf_counter() - t0)
+        res[name] = (ru, rb)
+    if rr.available():
+        with tempfile.TemporaryDirectory() as d:
+            t0 = time.perf_counter()
+            rr.users_business(ex, G, d)
+            legs['c1_reference_own_code_pairs_per_s'] = s / (time.perf_counter() - t0)
+            files = [json.load(open(os.path.join(d, n + '.json')))
+                     for n in ('u_cn', 'u_jaccard', 'u_adamic', 'b_cn', 'b_jaccard', 'b_adamic')]
+        ru, rb = res['faithful']
+        same = True
+        for got, want in zip(files, list(ru) + list(rb)):
+            for u in want:
+                for v in want[u]:
+                    x, y = got[u][v], want[u][v]
+                    same = same and (x == y or abs(x - y) <= 1e-12 * abs(y)) and type(x) is type(y)
+            same = same and got.keys() == dict(want).keys()
+        legs['c1_reference_own_code_equals_restatement'] = bool(same)
+        legs['c1_reference_own_code'] = ('oracle/_ref: the reference\'s similarity.py users()+business() '
+                                         'executed as they are (list membership, per-pair prints '
+                                         'swallowed, JSON dumps included), SNAP stand-in')
+    else:
+        legs['c1_reference_own_code'] = 'oracle/_ref not built on this machine'
+    t0 = time.perf_counter()
+    ob.score_pair_arrays(cfg['n_users'], cfg['n_biz'], eu, eb, pu, pv)
+    legs['c1_vectorised_oracle_b_pairs_per_s'] = pu.size / (time.perf_counter() - t0)
+    legs['c1_vectorised_sample'] = 'all %d pairs of C1, scipy.sparse algebra, one process' % pu.size
+    return legs
+
+
+def cpu_c_port(cfg, eu, eb, pu, pv, cores):
+    """The plain-C restatement: one thread on the first 1M pairs, then ALL pairs on every core
+    (its output is kept and compared with the GPU's)."""
+    from oracle import c_oracle
+    sides = {}
+    m = min(int(pu.size), 1_000_000)
+    t0 = time.perf_counter()
+    c_oracle.score_pair_arrays(cfg['n_users'], cfg['n_biz'], eu, eb, pu[:m], pv[:m])
+    sides['c_port_1thread_pairs_per_s'] = m / (time.perf_counter() - t0)
+    sides['c_port_sample'] = 'first %d pairs, graph build included' % m
+    t0 = time.perf_counter()
+    full = c_oracle.score_pair_arrays_parallel(cfg['n_users'], cfg['n_biz'], eu, eb, pu, pv,
+                                               threads=cores)
+    sides['c_port_all_cores_pairs_per_s'] = int(pu.size) / (time.perf_counter() - t0)
+    sides['c_port_all_cores_sample'] = ('all %d pairs in %d contiguous slices, one thread each, '
+                                        'graph build included in every slice' % (pu.size, cores))
+    return sides, full
+
+
+def compare_with_oracle(host, want):
+    """Bit-exact integers and jaccard, adamic within 1e-8 relative (bar: 1e-6)."""
+    bad = {}
+    for k in ('u_cn', 'b_cn', 'pa', 'u_union', 'b_union'):
+        if k in host:
+            d = int((host[k].astype(np.int64) != want[k].astype(np.int64)).sum())
+            if d:
+                bad[k] = d
+    for k in ('u_jaccard', 'b_jaccard'):
+        if k in host:
+            d = int((host[k] != want[k]).sum())
+            if d:
+                bad[k] = d
+    worst = 0.0
+    for k in ('u_adamic', 'b_adamic'):
+        if k in host:
+            nz = want[k] != 0
+            if ((host[k] == 0) != (want[k] == 0)).any():
+                bad[k] = 'zero pattern'
+            if nz.any():
+                worst = max(worst, float(np.max(np.abs(host[k][nz] - want[k][nz]) / want[k][nz])))
+    if worst > 1e-8:
+        bad['adamic_rel'] = worst
+    return {'rows': int(len(want['pa'])), 'mismatches': bad, 'adamic_max_rel_err': worst,
+            'ok': not bad}
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -215,6 +322,13 @@ class ClockSampler(object):
             self.proc.terminate()
 
 
+def _profile_json(name):
+    try:
+        return json.load(open(os.path.join(ROOT, 'profiles', name)))
+    except (OSError, ValueError):
+        return None
+
+
 # ------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -243,24 +357,26 @@ def main():
 
     synth = pkg('synth')
     cfg = dict(synth.CONFIGS[a.config])
-    per_gpu = a.pairs or cfg['n_pairs']
+    # C5 is defined over 8 GPUs (1B pairs): one GPU's share is an eighth of the list
+    per_gpu = a.pairs or (cfg['n_pairs'] // 8 if a.config == 'C5' else cfg['n_pairs'])
     workload = ('%s: %d users x %d businesses, %d review lines, %d candidate pairs per GPU '
                 '(K=%d per example user), seeded synthetic Yelp-shaped' %
                 (a.config, cfg['n_users'], cfg['n_biz'], cfg['n_reviews'], per_gpu, cfg['k']))
     config = {'workload': workload, 'name': a.config, 'pairs_per_gpu': per_gpu,
-              'outputs_per_pair': 9, 'l2': 'L2 flushed (256 MiB write) before every timed step',
-              'sharding': 'adjacency replicated per GPU; every rank scores its own shard of '
-                          'pairs_per_gpu pairs (drawn like the N=1 workload, seed 1+rank); no '
-                          'collective in the timed region'}
+              'outputs_per_pair': 7, 'l2': 'L2 flushed (256 MiB write) before every timed step'}
+    if world > 1:
+        config['sharding'] = ('ONE list of %d x %d pairs (N shards drawn like the N=1 workload, '
+                              'seed 1+shard, concatenated) cut by dist.shard_bounds into '
+                              'user-aligned work-balanced slices; adjacency replicated; results of '
+                              'every rank stored by the scoring kernels into rank 0\'s peer-mapped '
+                              'window (NVLink) inside the timed region' % (world, per_gpu))
     cores = len(os.sched_getaffinity(0))
 
-    # every rank generates the same graph and its own pair shard.  Weak scaling: each shard is
-    # drawn exactly like the N=1 workload (same K, same sampler, seed 1+rank), so the per-GPU work
-    # does not change shape with N; rank 0's shard IS the N=1 workload.
     eu, eb = synth.make_graph(seed=0, **cfg)
     deg = synth.degrees(cfg['n_users'], cfg['n_biz'], eu, eb)
     pcfg = dict(cfg)
     pcfg['n_pairs'] = per_gpu
+    # shard `rank` of the job, drawn exactly like the N=1 workload (rank 0's shard IS the N=1 workload)
     pu, pv = synth.make_pairs(edge_u=eu, edge_b=eb, seed=1 + rank, deg=deg, **pcfg)
 
     ug = a.cpu_user_groups or 600 * cores
@@ -272,9 +388,13 @@ def main():
         t0 = time.perf_counter()
         vals = []
         for _ in range(max(1, min(a.steps, 2))):
-            rate, sample, sides = cpu_reference(cfg, eu, eb, pu, pv, ug, bg, cores)
+            rate, sample, sides = cpu_reference_all_cores(cfg, eu, eb, pu, pv, ug, bg, cores)
             vals.append(rate)
         rate = statistics.median(vals)
+        try:
+            sides.update(cpu_c1_legs())
+        except Exception as exc:
+            sides['c1_legs_error'] = repr(exc)
         line = {'metric': METRIC, 'value': rate, 'unit': UNIT, 'impl': 'reference',
                 'n_gpus': a.gpus, 'steps': len(vals), 'warmup': 0,
                 'ms_per_step': (time.perf_counter() - t0) * 1e3 / len(vals),
@@ -287,16 +407,28 @@ def main():
         print(json.dumps(line), flush=True)
         return
 
-    cpu_baseline = None
+    cpu_baseline, c_full = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        # before CUDA is initialised in this process (the baseline forks workers)
-        rate, sample, sides = cpu_reference(cfg, eu, eb, pu, pv, ug, bg, cores)
-        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+        # single-process figure first (the >=100x target is judged on it)
+        sg_u = a.cpu_user_groups or 1500
+        sg_b = a.cpu_biz_groups or 600
+        rate, sample, sides = cpu_single_process(cfg, eu, eb, pu, pv, sg_u, sg_b)
+        try:
+            sides.update(cpu_c1_legs())
+        except Exception as exc:
+            sides['c1_legs_error'] = repr(exc)
+        try:
+            cs, c_full = cpu_c_port(cfg, eu, eb, pu, pv, cores)
+            sides.update(cs)
+        except Exception as exc:   # the C oracle is context and checker, never the headline
+            sides['c_port_error'] = repr(exc)
+        sides['all_core_python'] = 'see the --impl reference line of the same round (Oracle A on every core)'
+        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'host_cores': cores,
                         'sample': sample, 'note': NOTE, 'sides': sides}
 
     import torch
     import torch.distributed as dist
-    graph, roofline, _lib = pkg('graph'), pkg('roofline'), pkg('_lib')
+    graph, roofline, _lib, dmod = pkg('graph'), pkg('roofline'), pkg('_lib'), pkg('dist')
     _lib.load()   # fails loudly when the CUDA extension is missing
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -317,22 +449,68 @@ def main():
     build_device_s = time.perf_counter() - t0
     Gd.close()
     del deu, deb
-    n = int(pu.size)
-    d_u = torch.from_numpy(pu).to(dev)
-    d_b = torch.from_numpy(pv).to(dev)
-    outs = None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step(concurrent=False):
-        # the public device-resident call: both sides + pa, one side after the other on one
-        # stream, so that the per-kernel event times below are those of the kernels alone
-        nonlocal outs
-        outs = G.score_pairs(d_u, d_b, out=outs, concurrent=concurrent)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- the job's pair list.  N=1: this rank's shard.  N>1: all shards, concatenated, re-cut.
+    n_total = per_gpu * world
+    window, bounds, lo = None, None, 0
+    if world > 1:
+        shard_u = torch.from_numpy(pu).to(dev)
+        shard_b = torch.from_numpy(pv).to(dev)
+        all_u = torch.empty(n_total, dtype=torch.int32, device=dev)
+        all_b = torch.empty(n_total, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_u, shard_u)
+        dist.all_gather_into_tensor(all_b, shard_b)
+        pu_all, pv_all = all_u.cpu().numpy(), all_b.cpu().numpy()
+        del shard_u, shard_b
+        cost = dmod.pair_costs(pu_all, pv_all, deg[0], deg[1])
+        bounds = dmod.shard_bounds(pu_all, world, cost)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        d_u, d_b = all_u[lo:hi].clone(), all_b[lo:hi].clone()
+        pu, pv = pu_all[lo:hi], pv_all[lo:hi]              # this rank's slice from here on
+        if rank != 0:
+            del all_u, all_b
+        window = dmod.ResultWindow(G, n_total, columns=dmod.REFERENCE_COLUMNS, dst=0)
+    else:
+        d_u = torch.from_numpy(pu).to(dev)
+        d_b = torch.from_numpy(pv).to(dev)
+    n = int(d_u.numel())
+    outs = None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(concurrent=False, local=False):
+        # the public device-resident call: both sides + pa, one side after the other on one
+        # stream, so that the per-kernel event times below are those of the kernels alone
+        nonlocal outs
+        if window is not None and not local:
+            dmod.score_into_window(G, d_u, d_b, window, lo)
+        else:
+            outs = G.score_pairs(d_u, d_b, out=outs, concurrent=concurrent)
+
+    def timed(reps, **kw):
+        """Sum of per-step CUDA-event times of this rank, and the per-kernel stats."""
+        tot, st_u, st_b = 0.0, [], []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(**kw)
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+            st_u.append(G.score_stats(_lib.SIDE_USER))
+            st_b.append(G.score_stats(_lib.SIDE_BUSINESS))
+        return tot, st_u, st_b
 
     for _ in range(a.warmup):
         flush.zero_()
@@ -340,109 +518,100 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     time.sleep(0.3 if sampler else 0.0)
-    total_ms, score_ms_u, score_ms_b, group_ms, light_ms_u, light_ms_b = 0.0, [], [], [], [], []
-    launches = 0
     barrier()
     t_wall0 = time.perf_counter()
-    for _ in range(a.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step()
-        e1.record()
-        e1.synchronize()
-        total_ms += e0.elapsed_time(e1)
-        su, sb = G.score_stats(_lib.SIDE_USER), G.score_stats(_lib.SIDE_BUSINESS)
-        score_ms_u.append(su['score_ms'])
-        score_ms_b.append(sb['score_ms'])
-        light_ms_u.append(su['light_ms'])
-        light_ms_b.append(sb['light_ms'])
-        group_ms.append(su['group_ms'] + sb['group_ms'])
-        launches += su['kernel_launches'] + sb['kernel_launches']
-    barrier()
+    total_ms, st_u, st_b = timed(a.steps)
+    barrier()                              # N>1: every rank's rows are on rank 0 from here on
     t_wall1 = time.perf_counter()
     clocks = sampler.window(t_wall0, t_wall1) if sampler else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / a.steps
-    value = n * world / (ms_per_step * 1e-3)
+    ms_per_step = reduce_max(total_ms) / a.steps
+    value = n_total / (ms_per_step * 1e-3)
+    wall_ms_per_step = reduce_max((t_wall1 - t_wall0) * 1e3) / a.steps
+    launches = sum(s['kernel_launches'] for s in st_u + st_b)
+    score_ms_u = [s['score_ms'] for s in st_u]
+    score_ms_b = [s['score_ms'] for s in st_b]
+    light_ms_u = [s['light_ms'] for s in st_u]
+    light_ms_b = [s['light_ms'] for s in st_b]
+    group_ms = [x['group_ms'] + y['group_ms'] for x, y in zip(st_u, st_b)]
+    su, sb = st_u[-1], st_b[-1]
 
-    # ---- supplementary: the same call with the two sides on two streams (grids overlap)
-    for _ in range(6):          # the two-stream pattern grows the stream-ordered pool first
-        step(concurrent=True)
-    barrier()
-    c_ms = 0.0
-    c_reps = max(3, min(a.steps, 10))
-    for _ in range(c_reps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step(concurrent=True)
-        e1.record()
-        e1.synchronize()
-        c_ms += e0.elapsed_time(e1)
-    barrier()
-    ct = torch.tensor([c_ms / c_reps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ct, op=dist.ReduceOp.MAX)
-    concurrent_sides = {'ms_per_step': float(ct.item()), 'value': n * world / (float(ct.item()) * 1e-3),
-                        'unit': UNIT, 'steps': c_reps,
-                        'what': 'score_pairs(concurrent=True): business side on a second stream'}
-
-    # ---- final gather of the result records over NCCL (north_star), timed on its own
-    gather = None
-    if world > 1:
-        srcs = [outs[k] for k in sorted(outs)]
-        dsts = [[torch.empty_like(s) for _ in range(world)] if rank == 0 else None for s in srcs]
-        for _ in range(2):
-            for s, d in zip(srcs, dsts):
-                dist.gather(s, d, dst=0)
+    concurrent_sides, multi = None, None
+    reps = max(3, min(a.steps, 10))
+    if world == 1:
+        # ---- supplementary: the same call with the two sides on two streams (grids overlap)
+        for _ in range(6):          # the two-stream pattern grows the stream-ordered pool first
+            step(concurrent=True)
         barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for s, d in zip(srcs, dsts):
-            dist.gather(s, d, dst=0)
-        g1.record()
-        torch.cuda.synchronize()
-        gt = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        gms = float(gt.item())
-        gather = {'ms': gms, 'bytes_into_rank0': 56 * n * (world - 1),
-                  'value_with_gather': n * world / ((ms_per_step + gms) * 1e-3), 'unit': UNIT,
-                  'backend': 'nccl gather, not overlapped'}
-        del dsts
-        # the same with the gather overlapped: score in 4 slices, gather slice k on a side stream
-        # while slice k+1 is being scored (dist.score_and_gather_overlapped)
-        dmod = pkg('dist')
-        o2 = r2 = None
+        c_ms, _, _ = timed(reps, concurrent=True)
+        c_ms /= reps
+        concurrent_sides = {'ms_per_step': c_ms, 'value': n_total / (c_ms * 1e-3), 'unit': UNIT,
+                            'steps': reps,
+                            'what': 'score_pairs(concurrent=True): business side on a second stream'}
+    else:
+        # ---- the two comparison arms: scoring into local memory, and local scoring + NCCL gather
         for _ in range(2):
-            o2, r2 = dmod.score_and_gather_overlapped(G, d_u, d_b, chunks=4, out=o2, recv=r2)
+            step(local=True)
         barrier()
-        tot = 0.0
-        reps = max(3, min(a.steps, 10))
+        l_ms, _, _ = timed(reps, local=True)
+        barrier()
+        l_ms = reduce_max(l_ms) / reps
+        counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
+        keep = {k: outs[k] for k in dmod.REFERENCE_COLUMNS}
+        full = None
+        if rank == 0:
+            full = {k: torch.empty(n_total, dtype=keep[k].dtype, device=dev) for k in keep}
+        for _ in range(2):
+            dmod.gather_results(keep, counts, dst=0, out=full)
+        barrier()
+        g_tot = 0.0
         for _ in range(reps):
-            flush.zero_()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
-            o2, r2 = dmod.score_and_gather_overlapped(G, d_u, d_b, chunks=4, out=o2, recv=r2)
+            dmod.gather_results(keep, counts, dst=0, out=full)
             g1.record()
             g1.synchronize()
-            tot += g0.elapsed_time(g1)
+            g_tot += g0.elapsed_time(g1)
         barrier()
-        gt = torch.tensor([tot / reps], dtype=torch.float64, device=dev)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        oms = float(gt.item())
-        gather['overlapped'] = {'ms_per_step': oms, 'value': n * world / (oms * 1e-3), 'unit': UNIT,
-                                'chunks': 4, 'steps': reps,
-                                'what': 'scoring of all ranks + final NCCL gather into rank 0, '
-                                        'gather of slice k overlapped with scoring of slice k+1'}
+        g_ms = reduce_max(g_tot) / reps
+        bpp = window.bytes_per_pair()
+        multi = {'bytes_per_pair_over_nvlink': bpp,
+                 'bytes_into_rank0_per_step': bpp * (n_total - n if rank == 0 else 0),
+                 'slice_pairs': counts,
+                 'fused_window': {'ms_per_step': ms_per_step, 'value': value, 'unit': UNIT,
+                                  'wall_ms_per_step_with_barriers': wall_ms_per_step,
+                                  'what': 'every rank\'s kernels store its rows into rank 0\'s '
+                                          'peer-mapped window (this is the line\'s `value`)'},
+                 'scoring_only': {'ms_per_step': l_ms, 'value': n_total / (l_ms * 1e-3), 'unit': UNIT,
+                                  'what': 'same slices scored into local memory, nothing gathered'},
+                 'nccl_gather': {'gather_ms': g_ms, 'ms_per_step': l_ms + g_ms,
+                                 'value': n_total / ((l_ms + g_ms) * 1e-3), 'unit': UNIT,
+                                 'what': 'local scoring, then dist.gather_results: one grouped batch '
+                                         'of NCCL send/recv of the seven columns into rank 0'}}
+        # ---- every rank's rows, as they sit on rank 0, against the unsharded call and the oracle
         if rank == 0:
-            same = all(torch.equal(r2[k][0], outs[k]) for k in outs)
-            gather['overlapped']['rank0_rows_match_unsharded_call'] = bool(same)
-        del o2, r2
+            cols = window.tensors()
+            whole = G.score_pairs(all_u, all_b)
+            torch.cuda.synchronize()
+            multi['all_rows_match_unsharded_call'] = bool(all(torch.equal(cols[k], whole[k]) for k in cols))
+            multi['nccl_gather_rows_match'] = bool(all(torch.equal(cols[k], full[k]) for k in cols))
+            del whole
+            try:
+                from oracle import c_oracle
+                idx = np.arange(0, n_total, max(1, n_total // 200_000))
+                want = c_oracle.score_pair_arrays_parallel(cfg['n_users'], cfg['n_biz'], eu, eb,
+                                                           pu_all[idx], pv_all[idx], threads=cores)
+                tidx = torch.from_numpy(idx).to(dev)
+                got = {k: cols[k][tidx].cpu().numpy() for k in cols}
+                chk = compare_with_oracle(got, want)
+                chk['what'] = ('strided sample over the whole %d-pair list (rows of every rank) vs the C '
+                               'oracle' % n_total)
+                multi['oracle_check'] = chk
+            except Exception as exc:
+                multi['oracle_check'] = {'error': repr(exc)}
+            del full
+        outs = None
 
-    # ---- end to end through the host-buffer API
+    # ---- end to end through the host-buffer API (the seven reference outputs: 48 B per pair)
     sess = G.host_session(n)
     hu, hb = sess.pinned_inputs(n)
     hu[:] = pu
@@ -455,14 +624,14 @@ def main():
     for _ in range(e2e_steps):
         host = sess.score_pinned(n)
     torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_s = float(dt.item()) / e2e_steps
-    e2e = {'value': n * world / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
+    e2e_s = reduce_max(time.perf_counter() - t0) / e2e_steps
+    link = sess.measure_link(n) if rank == 0 else None
+    e2e = {'value': n_total / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
            'h2d_bytes_per_step': sess.h2d_bytes_per_pair * n,
            'd2h_bytes_per_step': sess.d2h_bytes_per_pair * n, 'steps': e2e_steps,
-           'api': 'BipartiteGraph.host_session().score_pinned -> one blp_score_pairs_host call (pinned host buffers in and out, both sides + pa)'}
+           'columns': list(sess.KEYS), 'link': link,
+           'api': 'BipartiteGraph.host_session().score_pinned -> one blp_score_pairs_host call '
+                  '(pinned host buffers in and out, both sides + pa; per rank at N>1)'}
 
     if rank == 0:
         peaks = {}
@@ -473,15 +642,19 @@ def main():
         peak = float(peaks.get('hbm_gbs', 6650.0))
         ab = roofline.algorithmic_bytes(cfg['n_users'], cfg['n_biz'], eu, eb, pu, pv,
                                         host['u_cn'], host['b_cn'])
+        parity = None
+        if c_full is not None:
+            parity = compare_with_oracle(host, c_full)
+            parity['what'] = ('ALL %d pairs of the timed workload: blp_score_pairs_host output vs the '
+                              'plain-C oracle (oracle/blp_oracle.c)' % n)
         traffic, traffic_src, phase = None, None, None
-        try:
-            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
-            if a.config == 'C2' and per_gpu == cfg['n_pairs']:   # the capture is of this workload
-                traffic = tj['user_side']['traffic_bytes']
-                traffic_src = tj['source']
-                phase = tj.get('phase_shares_user_side')
-        except (OSError, ValueError, KeyError):
-            pass
+        tj = _profile_json('r02_traffic.json')
+        if tj and a.config == tj.get('config', 'C2') and per_gpu == cfg['n_pairs'] and world == 1:
+            traffic = tj['user_side']['traffic_bytes']     # the capture is of this workload
+            traffic_src = tj['source']
+        pj = _profile_json('r02_phase_shares.json')
+        if pj and a.config == pj.get('config', 'C2'):
+            phase = pj
         ku_ms = statistics.mean(score_ms_u)
         kb_ms = statistics.mean(score_ms_b)
         bytes_u = ab['user'] + ab['pa']
@@ -499,17 +672,19 @@ def main():
                 'work_items': {'user_side': su['n_groups'], 'user_side_warp_kernel': su['light_groups'],
                                'business_side': sb['n_groups'],
                                'business_side_warp_kernel': sb['light_groups']},
+                'launch': {'ctas': su['ctas'], 'threads_per_cta': su['threads_per_cta'],
+                           'smem_bytes': su['smem_bytes'], 'range_passes': su['range_passes']},
                 'business_kernel': {'kernel_ms': kb_ms,
                                     'k_score_light_ms': statistics.mean(light_ms_b),
                                     'algorithmic_bytes_per_launch':
                                     ab['business'],
                                     'achieved': ab['business'] / (kb_ms * 1e-3) / 1e9},
                 'grouping_ms_per_step': statistics.mean(group_ms),
-                'note': 'graph (26 MB + hub bitmaps) is L2-resident: DRAM traffic is far below the '
+                'note': 'the graph is L2-resident for C1-C4: DRAM traffic is far below the '
                         'algorithmic bytes; the kernels are latency/issue-bound, and the probe / table '
                         'paths answer hub-partner pairs without streaming the partner list, so the '
                         'algorithmic figure credits bytes the implementation does not move -- see '
-                        'profiles/r01_notes.md.',
+                        'profiles/r02_notes.md.',
                 'whole_step': {'algorithmic_bytes': ab['total'],
                                'achieved': ab['total'] / (ms_per_step * 1e-3) / 1e9},
                 'bytes_breakdown': {k: ab[k] for k in ('expansion_user', 'stream_user',
@@ -518,21 +693,32 @@ def main():
         if phase:
             # "for the intersection kernel use the per-pair terms only over K2's own
             # time".  Expansion and intersection are fused in one launch here, so K2's own time is
-            # DERIVED: this run's kernel time x the intersection sweep's share of CTA cycles,
-            # measured once with the instrumented build (tools/phase_time.py).
-            t_int = ku_ms * phase['intersection_sweep']
+            # DERIVED: this run's kernel time x the intersection phase's share of the CTA kernel's
+            # cycles, measured with the instrumented build of the SAME kernels (tools/phase_time.py).
+            share = phase['intersection_share_of_user_side']
+            t_int = ku_ms * share
             roof['intersection_phase'] = {
-                'derived': True, 'share_of_kernel': phase['intersection_sweep'],
+                'derived': True, 'share_of_kernel': share,
                 'share_source': phase['source'], 'time_ms': t_int,
                 'algorithmic_bytes': ab['stream_user'],
                 'achieved': ab['stream_user'] / (t_int * 1e-3) / 1e9,
                 'frac': ab['stream_user'] / (t_int * 1e-3) / 1e9 / peak}
+        if cpu_baseline:
+            fair1 = cpu_baseline['value']
+            cpu_baseline['target_100x'] = {
+                'vs_fair_single_process': {'device_resident': value / fair1,
+                                           'e2e': e2e['value'] / fair1},
+                'vs_c_port_all_cores': None}
+            allc = cpu_baseline['sides'].get('c_port_all_cores_pairs_per_s')
+            if allc:
+                cpu_baseline['target_100x']['vs_c_port_all_cores'] = {
+                    'device_resident': value / allc, 'e2e': e2e['value'] / allc}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps,
                 'warmup': a.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic',
                 'config': config, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
-                'roofline': roof, 'cpu_baseline': cpu_baseline, 'gather': gather,
-                'concurrent_sides': concurrent_sides,
+                'roofline': roof, 'cpu_baseline': cpu_baseline, 'parity_full_workload': parity,
+                'multi_gpu': multi, 'concurrent_sides': concurrent_sides,
                 'graph': G.info(),
                 'graph_build': {'host_builder_s': build_host_s, 'device_builder_s': build_device_s,
                                 'edge_lines': int(eu.size),
@@ -542,6 +728,8 @@ def main():
     if sampler:
         sampler.stop()
     if world > 1:
+        barrier()
+        window.close()
         dist.destroy_process_group()
 
 

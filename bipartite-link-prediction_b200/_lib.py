@@ -12,7 +12,8 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, 'csrc')
 INCLUDE = os.path.join(_ROOT, 'include')
 LIB_PATH = os.path.join(_HERE, 'libblp.so')
-SOURCES = ('blp_graph.cu', 'blp_build.cu', 'blp_score.cu', 'blp_host.cu', 'blp_hop3.cu', 'blp_eval.cu')
+SOURCES = ('blp_graph.cu', 'blp_build.cu', 'blp_score.cu', 'blp_host.cu', 'blp_hop3.cu', 'blp_eval.cu',
+           'blp_peer.cu')
 
 BLP_OK = 0
 BLP_ERR_INVALID, BLP_ERR_CUDA, BLP_ERR_OOM, BLP_ERR_RANGE, BLP_ERR_UNSUPPORTED = -1, -2, -3, -4, -5
@@ -23,7 +24,9 @@ EXPORTS = ('blp_version', 'blp_last_error', 'blp_device_count', 'blp_graph_creat
            'blp_graph_destroy', 'blp_graph_info', 'blp_graph_degrees', 'blp_score_pairs',
            'blp_score_stats', 'blp_graph_reserve_sms', 'blp_graph_create_device',
            'blp_hop3_count', 'blp_hop3_fill', 'blp_eval_precision_at_k', 'blp_eval_roc_auc',
-           'blp_score_pairs_host')
+           'blp_score_pairs_host', 'blp_peer_alloc', 'blp_peer_open', 'blp_peer_close',
+           'blp_peer_free')
+IPC_HANDLE_BYTES = 64
 
 
 class GraphInfo(ctypes.Structure):
@@ -125,6 +128,11 @@ def load():
                                           ctypes.c_int64] + [ctypes.c_void_p] * 9 + [ctypes.c_int] * 3)
     lib.blp_score_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ScoreStats)]
     lib.blp_graph_reserve_sms.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.blp_peer_alloc.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p),
+                                   ctypes.c_char_p]
+    lib.blp_peer_open.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.blp_peer_close.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    lib.blp_peer_free.argtypes = [ctypes.c_int, ctypes.c_void_p]
     for name in EXPORTS:
         if name not in ('blp_last_error',):
             getattr(lib, name).restype = ctypes.c_int

@@ -426,10 +426,13 @@ extern "C" int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n
         set_error("blp_graph_create_device: device index out of range");
         return BLP_ERR_INVALID;
     }
-    BLP_CUDA_TRY(cudaSetDevice(device));
+    BLP_ON_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
     const long long n = n_edges;
-    const int grid = 148 * 8;
+    int sm_query = 0;
+    if (cudaDeviceGetAttribute(&sm_query, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sm_query <= 0)
+        sm_query = 132;
+    const int grid = sm_query * 8;
 
     blp_graph* g = new (std::nothrow) blp_graph();
     if (!g) {
@@ -580,7 +583,7 @@ extern "C" int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n
                                                              (unsigned long long*)g->u_row, g->u_deg);
     k_row_descriptors<<<(n_biz + 255) / 256, 256, 0, st>>>(b_off, b_deg, n_biz,
                                                            (unsigned long long*)g->b_row, g->b_deg);
-    if (!getenv("BLP_NO_BANK_STRIPE")) {
+    if (g->tune.bank_stripe) {   // (BLP_NO_BANK_STRIPE, read at handle creation)
         k_bank_stripe<<<g->sm_count * 4, 256, 0, st>>>(u_off, u_deg, n_users, g->u_adj, tmp, next_row);
         k_bank_stripe<<<g->sm_count * 4, 256, 0, st>>>(b_off, b_deg, n_biz, g->b_adj, tmp, next_row + 1);
     }

@@ -17,6 +17,17 @@
 namespace blp {
 namespace {
 
+// SM count of the device the buffers live on (= the caller's current device for these entry points)
+long long current_sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+        (void)cudaGetLastError();
+        sms = 132;
+    }
+    return sms;
+}
+
 constexpr unsigned kEvalAll = 0xffffffffu;
 
 __global__ void k_precision_at_k(const long long* __restrict__ off, const int* __restrict__ labels,
@@ -109,7 +120,8 @@ extern "C" int blp_eval_precision_at_k(const int64_t* offsets, const int32_t* la
         return BLP_ERR_INVALID;
     }
     if (n_groups == 0) return BLP_OK;
-    const int blocks = (int)std::min<long long>((n_groups * 32 + 255) / 256, 148LL * 16);
+    const long long sms = blp::current_sm_count();
+    const int blocks = (int)std::min<long long>((n_groups * 32 + 255) / 256, sms * 16);
     blp::k_precision_at_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(
         (const long long*)offsets, labels, scores, n_groups, k, precision_out);
     BLP_CUDA_TRY(cudaGetLastError());
@@ -143,7 +155,8 @@ extern "C" int blp_eval_roc_auc(const int32_t* labels, const double* scores, int
     BLP_TRY_E(cudaMallocAsync((void**)&tmp, sizeof(unsigned long long) * (size_t)n, st));
     BLP_TRY_E(cudaMallocAsync((void**)&counters, sizeof(unsigned long long) * 4, st));
     BLP_TRY_E(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 4, st));
-    const int blocks = (int)std::min<long long>((n + 255) / 256, 148LL * 16);
+    const long long sms = current_sm_count();
+    const int blocks = (int)std::min<long long>((n + 255) / 256, sms * 16);
     k_split_by_label<<<blocks, 256, 0, st>>>(labels, scores, n, pos, neg, counters);
     unsigned long long h[4] = {0, 0, 0, 0};
     BLP_TRY_E(cudaMemcpyAsync(h, counters, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, st));
@@ -154,7 +167,7 @@ extern "C" int blp_eval_roc_auc(const int32_t* labels, const double* scores, int
         unsigned long long* sorted = neg;
         rc = radix_sort_u64(neg, tmp, (long long)h[1], shifts, st, &sorted);
         if (rc != BLP_OK) return done(rc);
-        const int b2 = (int)std::min<long long>(((long long)h[0] + 255) / 256, 148LL * 16);
+        const int b2 = (int)std::min<long long>(((long long)h[0] + 255) / 256, sms * 16);
         k_auc_counts<<<b2, 256, 0, st>>>(pos, (long long)h[0], sorted, (long long)h[1], counters);
         BLP_TRY_E(cudaGetLastError());
     }

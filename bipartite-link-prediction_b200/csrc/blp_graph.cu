@@ -139,14 +139,24 @@ int init_device_state(blp_graph* g, int device) {
     g->device = device;
     g->sm_count = prop.multiProcessorCount;
     g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-    // keep stream-ordered scratch cached in the pool instead of returning it to the driver at
-    // every synchronisation (the default release threshold is 0)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    read_tuning(&g->tune);
+    // a pool of the handle's own for the stream-ordered scratch of its scoring calls, kept cached
+    // instead of being returned to the driver at every synchronisation (release threshold = max);
+    // the device's default pool keeps its settings
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&g->pool, &props) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(g->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            g->pool = nullptr;   // fall back to the default pool, untouched
+        }
+        (void)cudaGetLastError();
     }
-    (void)cudaGetLastError();
     for (int sd = 0; sd < 2; ++sd)
         for (int k = 0; k < 4; ++k) BLP_CUDA_TRY(cudaEventCreate(&g->ev[sd][k]));
     for (int sd = 0; sd < 2; ++sd)
@@ -157,6 +167,16 @@ int init_device_state(blp_graph* g, int device) {
         BLP_CUDA_TRY(cudaMemset(g->d_counts[sd], 0, sizeof(int) * 2));
     }
     return BLP_OK;
+}
+
+void read_tuning(blp_tuning* t) {
+    if (const char* e = getenv("BLP_RANGES")) t->ranges = atoi(e);
+    if (const char* e = getenv("BLP_GROUPING"))
+        t->grouping = !strcmp(e, "runs") ? 1 : (!strcmp(e, "sort") ? 0 : -1);   // MODE_RUNS / MODE_SORT
+    if (const char* e = getenv("BLP_NT")) t->nt = atoi(e);
+    if (const char* e = getenv("BLP_LIGHT_STREAM")) t->light_stream = atoi(e) != 0;
+    if (const char* e = getenv("BLP_SLICE_GROWTH")) t->slice_growth = atof(e);
+    if (getenv("BLP_NO_BANK_STRIPE")) t->bank_stripe = false;
 }
 
 // 1/ln(d) in Q1.31 for d = 0..max_deg (0 for d <= 1), evaluated with the host libm.
@@ -207,7 +227,7 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
         blp::set_error("blp_graph_create: device index out of range");
         return BLP_ERR_INVALID;
     }
-    BLP_CUDA_TRY(cudaSetDevice(device));
+    BLP_ON_DEVICE(device);
 
     blp_graph* g = nullptr;
     try {
@@ -259,7 +279,9 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
             }
         }
         std::vector<uint64_t>().swap(keys);
-        if (!getenv("BLP_NO_BANK_STRIPE")) {   // tuning switch
+        blp_tuning tune;
+        blp::read_tuning(&tune);
+        if (tune.bank_stripe) {   // (BLP_NO_BANK_STRIPE: tuning switch)
             std::vector<int32_t> tmp;
             std::vector<int32_t> bucket[32];
             for (int32_t u = 0; u < n_users; ++u)
@@ -329,7 +351,8 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
 
 extern "C" int blp_graph_destroy(blp_graph* g) {
     if (!g) return BLP_OK;
-    cudaSetDevice(g->device);
+    blp::DeviceGuard device_guard__(g->device);
+    cudaDeviceSynchronize();   // scratch of calls still in flight goes back to the pool first
     blp::host_state_destroy(g);
     cudaFree(g->u_row);
     cudaFree(g->b_row);
@@ -354,6 +377,7 @@ extern "C" int blp_graph_destroy(blp_graph* g) {
         if (g->ev_fork[sd]) cudaEventDestroy(g->ev_fork[sd]);
     if (g->side_stream) cudaStreamDestroy(g->side_stream);
     for (int sd = 0; sd < 2; ++sd) cudaFree(g->d_counts[sd]);
+    if (g->pool) cudaMemPoolDestroy(g->pool);
     (void)cudaGetLastError();
     delete g;
     return BLP_OK;
@@ -387,7 +411,7 @@ extern "C" int blp_graph_degrees(const blp_graph* g, int side, int32_t* host_out
         blp::set_error("blp_graph_degrees: bad argument");
         return BLP_ERR_INVALID;
     }
-    BLP_CUDA_TRY(cudaSetDevice(g->device));
+    BLP_ON_DEVICE(g->device);
     const int* src = side == BLP_SIDE_USER ? g->u_deg : g->b_deg;
     size_t n = (size_t)(side == BLP_SIDE_USER ? g->n_users : g->n_biz);
     BLP_CUDA_TRY(cudaMemcpy(host_out, src, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -410,7 +434,7 @@ extern "C" int blp_score_stats(const blp_graph* g, int side, blp_score_stats_t* 
     }
     *stats = g->stats[side];
     if (g->ev_recorded[side]) {
-        BLP_CUDA_TRY(cudaSetDevice(g->device));
+        BLP_ON_DEVICE(g->device);
         BLP_CUDA_TRY(cudaEventSynchronize(g->ev[side][2]));
         BLP_CUDA_TRY(cudaEventElapsedTime(&stats->group_ms, g->ev[side][0], g->ev[side][1]));
         BLP_CUDA_TRY(cudaEventElapsedTime(&stats->score_ms, g->ev[side][1], g->ev[side][2]));

@@ -143,7 +143,7 @@ int launch_hop3(blp_graph* g, Hop3Args a, bool fill, cudaStream_t st) {
         return BLP_ERR_UNSUPPORTED;
     }
     int* counter = nullptr;
-    BLP_CUDA_TRY(cudaMallocAsync((void**)&counter, sizeof(int), st));
+    BLP_CUDA_TRY(pool_alloc(g, (void**)&counter, sizeof(int), st));
     BLP_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), st));
     a.work_counter = counter;
     int per_sm = 0;
@@ -171,7 +171,7 @@ extern "C" int blp_hop3_count(blp_graph* g, const int32_t* users, int64_t n, int
         return BLP_ERR_INVALID;
     }
     if (n == 0) return BLP_OK;
-    BLP_CUDA_TRY(cudaSetDevice(g->device));
+    BLP_ON_DEVICE(g->device);
     blp::Hop3Args a{};
     a.users = users;
     a.n = n;
@@ -186,7 +186,7 @@ extern "C" int blp_hop3_fill(blp_graph* g, const int32_t* users, int64_t n, cons
         return BLP_ERR_INVALID;
     }
     if (n == 0) return BLP_OK;
-    BLP_CUDA_TRY(cudaSetDevice(g->device));
+    BLP_ON_DEVICE(g->device);
     blp::Hop3Args a{};
     a.users = users;
     a.n = n;

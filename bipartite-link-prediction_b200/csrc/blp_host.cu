@@ -97,7 +97,7 @@ extern "C" int blp_score_pairs_host(blp_graph* g, const int32_t* pair_u, const i
         return BLP_ERR_INVALID;
     }
     if (n == 0) return BLP_OK;
-    BLP_CUDA_TRY(cudaSetDevice(g->device));
+    BLP_ON_DEVICE(g->device);
     int rc = host_state_reserve(g, n);
     if (rc != BLP_OK) return rc;
     blp_host_state* h = g->host;
@@ -108,8 +108,7 @@ extern "C" int blp_score_pairs_host(blp_graph* g, const int32_t* pair_u, const i
     const int uc = std::max(1, std::min(user_slices > 0 ? user_slices : 5, max_slices));
     const int bc = std::max(1, std::min(biz_slices > 0 ? biz_slices : 2, max_slices));
     const int lead = std::max(0, std::min(lead_slices >= 0 ? lead_slices : 1, uc - 1));
-    double slice_growth = 0.0;
-    if (const char* e = getenv("BLP_SLICE_GROWTH")) slice_growth = atof(e);   // tuning override
+    const double slice_growth = g->tune.slice_growth;   // (BLP_SLICE_GROWTH, read at handle creation)
     // equal user-side slices by default; BLP_SLICE_GROWTH = g > 1 puts bound c at n * (c/uc)^g
     // (small first slice, larger later ones) -- measured slower on C2 for g = 1.5 and 2
     const double grow = slice_growth > 0 ? slice_growth : 1.0;

@@ -22,12 +22,28 @@
 
 struct blp_host_state;   // staging buffers and streams of blp_score_pairs_host (blp_host.cu)
 
+// BLP_* tuning variables (developer overrides).  Read ONCE, when a handle is created -- never on
+// the scoring path.
+struct blp_tuning {
+    int ranges = 0;            // BLP_RANGES: at least this many id-range passes
+    int grouping = -1;         // BLP_GROUPING=runs|sort: force a grouping mode (-1 = decide on the device)
+    int nt = 0;                // BLP_NT=256|512|1024: threads per CTA of k_score_side (0 = by size)
+    bool light_stream = true;  // BLP_LIGHT_STREAM=0: keep k_score_light on the caller's stream
+    double slice_growth = 0.0; // BLP_SLICE_GROWTH: user-side slice plan of blp_score_pairs_host
+    bool bank_stripe = true;   // BLP_NO_BANK_STRIPE: leave long rows in ascending order
+};
+
 struct blp_graph {
     blp_host_state* host = nullptr;
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;  // bytes of dynamic shared memory one CTA may opt in to
     int reserve_sms = 0;     // SMs left out of the persistent scoring grids
+    blp_tuning tune;         // developer overrides, read when the handle was created
+    // stream-ordered scratch of the scoring calls comes from a pool the handle owns (kept warm:
+    // release threshold = max), so the device's default pool and other libraries' allocators are
+    // left alone; destroyed with the handle
+    cudaMemPool_t pool = nullptr;
     // CTAs per SM of the scoring-kernel variants already configured: [nt 256/512/1024][ranged][rec]
     int occ_cache[3][2][2] = {};
     size_t occ_smem[3][2][2] = {};
@@ -36,16 +52,19 @@ struct blp_graph {
     int32_t n_users_in = 0, n_biz_in = 0, max_udeg = 0, max_bdeg = 0;
     int64_t device_bytes = 0;
     int64_t u_adj_len = 0, b_adj_len = 0;   // padded entries of u_adj / b_adj
-    // Both CSR directions.  Every row is padded to a multiple of
-    // four ids with the sentinel n_biz (user rows) / n_users (business rows), so every row starts
-    // 16-byte aligned and is read with 128-bit loads without a tail.
+    // Both CSR directions.  Every row is padded AT ITS TAIL to a multiple of four ids with the
+    // sentinel n_biz (user rows) / n_users (business rows), so every row starts 16-byte aligned and
+    // is read with 128-bit loads without a tail; the first deg(row) entries are the real ids
+    // (blp_hop3 and the light-kernel prefetch rely on that).  Rows of <= 16 ids ascend; longer rows
+    // are bank-striped (a permutation of the row, see bank_stripe_row) -- nothing may assume a
+    // sorted row, so no binary search over rows.
     // Row descriptors: (first padded entry / 4) << 24 | true degree -- one 8-byte load per list.
     // Bits 52..62 hold (hub-bitmap slot + 1) of a node whose neighbour list is also kept as a
     // bitmap (0 = none); they are set only when every first-entry index fits 28 bits.
     unsigned long long* u_row = nullptr;  // [n_users]
     unsigned long long* b_row = nullptr;  // [n_biz]
-    int* u_adj = nullptr;        // user -> businesses, ascending
-    int* b_adj = nullptr;        // business -> users, ascending
+    int* u_adj = nullptr;        // user -> businesses
+    int* b_adj = nullptr;        // business -> users
     int* u_deg = nullptr;        // true (unpadded, de-duplicated) degrees
     int* b_deg = nullptr;
     // Adamic-Adar weight 1/ln(deg(id)) (0 where deg <= 1 and in padding) of every adjacency
@@ -91,7 +110,34 @@ int radix_sort_u64(unsigned long long* keys, unsigned long long* tmp, long long 
                    const std::vector<int>& shifts, cudaStream_t st, unsigned long long** sorted);
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void read_tuning(blp_tuning* t);
+// stream-ordered scratch from the handle's own pool
+inline cudaError_t pool_alloc(blp_graph* g, void** p, size_t bytes, cudaStream_t st) {
+    return g->pool ? cudaMallocFromPoolAsync(p, bytes, g->pool, st) : cudaMallocAsync(p, bytes, st);
+}
+
+// Every entry point runs on the handle's device and leaves the caller's current device as it
+// found it (a process driving several GPUs must not find its device switched by a library call).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) err = cudaSetDevice(device);
+        else prev = -1;   // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 }  // namespace blp
+
+#define BLP_ON_DEVICE(dev)                                                                    \
+    blp::DeviceGuard device_guard__(dev);                                                     \
+    if (device_guard__.err != cudaSuccess)                                                    \
+        return blp::cuda_fail(device_guard__.err, "cudaSetDevice", __FILE__, __LINE__)
 
 #define BLP_CUDA_TRY(expr)                                                     \
     do {                                                                       \

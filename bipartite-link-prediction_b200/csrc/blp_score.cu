@@ -32,6 +32,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "blp_internal.h"
@@ -720,16 +721,31 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
 
 template <int NT, bool RANGED, bool REC>
 static int launch_side(const SideArgs& a, int grid, size_t smem, cudaStream_t st) {
-    // (the dynamic shared-memory opt-in for this size was made by occupancy<>() and is cached)
+    // (the dynamic shared-memory opt-in covers this size: raise_smem_optin<>() ran just before)
     k_score_side<NT, RANGED, REC><<<grid, NT, smem, st>>>(a);
     BLP_CUDA_TRY(cudaGetLastError());
     return BLP_OK;
 }
 
+// The dynamic shared-memory opt-in is a property of (kernel, device) for the whole PROCESS, not of
+// a graph handle: handles of different size share it.  It is kept in a process-wide table and only
+// ever raised, so a small graph scored between two calls on a large one cannot lower it.
+constexpr int kMaxDevices = 64;
+static std::mutex g_optin_mutex;
+template <int NT, bool RANGED, bool REC>
+static int raise_smem_optin(int device, size_t smem) {
+    static size_t granted[kMaxDevices] = {};
+    std::lock_guard<std::mutex> lock(g_optin_mutex);
+    if (device < 0 || device >= kMaxDevices || smem > granted[device]) {
+        BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_side<NT, RANGED, REC>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (device >= 0 && device < kMaxDevices) granted[device] = smem;
+    }
+    return BLP_OK;
+}
+
 template <int NT, bool RANGED, bool REC>
 static int occupancy(size_t smem, int* ctas_per_sm) {
-    BLP_CUDA_TRY(cudaFuncSetAttribute(k_score_side<NT, RANGED, REC>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BLP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         ctas_per_sm, k_score_side<NT, RANGED, REC>, NT, smem));
     return BLP_OK;
@@ -908,7 +924,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         set_error("blp_score_pairs: at most 2^31-2 pairs per call; split the pair list");
         return BLP_ERR_UNSUPPORTED;
     }
-    BLP_CUDA_TRY(cudaSetDevice(g->device));
+    BLP_ON_DEVICE(g->device);
     cudaStream_t st = (cudaStream_t)stream;
     blp_score_stats_t& stats = g->stats[side];
     stats = blp_score_stats_t{};
@@ -952,7 +968,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     const long long cap_words =
         (((long long)g->max_smem_optin - (long long)sizeof(TileSmem) - 256) / 4) & ~3LL;
     int n_ranges = (int)((full_words + cap_words - 1) / cap_words);
-    if (const char* e = getenv("BLP_RANGES")) n_ranges = std::max(n_ranges, atoi(e));
+    n_ranges = std::max(n_ranges, g->tune.ranges);   // (BLP_RANGES, read at handle creation)
     int range_words = full_words;
     if (n_ranges > 1) {
         range_words = (int)((((long long)full_words + n_ranges - 1) / n_ranges + 3) & ~3LL);
@@ -979,8 +995,8 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     unsigned char* arena = nullptr;
     size_t arena_used = 0;
     {
-        cudaError_t e = cudaMallocAsync((void**)&arena, arena_bytes, st);
-        if (e != cudaSuccess) return blp::cuda_fail(e, "cudaMallocAsync(scratch)", __FILE__, __LINE__);
+        cudaError_t e = pool_alloc(g, (void**)&arena, arena_bytes, st);
+        if (e != cudaSuccess) return blp::cuda_fail(e, "cudaMallocFromPoolAsync(scratch)", __FILE__, __LINE__);
         scratch.push_back(arena);
     }
     auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
@@ -1023,9 +1039,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     // no sort: the runs of equal keys are the work items when they average >= 4 pairs.  The
     // decision is taken on the device (k_decide_mode); the kernels of the mode not chosen exit at
     // once, so the call never waits for the host.
-    int force = -1;
-    if (const char* gmode = getenv("BLP_GROUPING"))   // "runs" / "sort": tuning override
-        force = !strcmp(gmode, "runs") ? MODE_RUNS : (!strcmp(gmode, "sort") ? MODE_SORT : -1);
+    int force = g->tune.grouping;   // (BLP_GROUPING=runs|sort, read at handle creation)
     if (!us && force < 0) force = MODE_SORT;   // a per-user list is never grouped by business
     int* mode = scalars + 3;
     if (force < 0) {
@@ -1101,8 +1115,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     // ---- persistent scoring grid: as many CTAs per SM as the bitmap allows
     int per_sm = 0, nt = 0, rc = BLP_OK;
     const size_t budget = (size_t)g->max_smem_optin;
-    const char* nt_env = getenv("BLP_NT");   // tuning override
-    const int nt_force = nt_env ? atoi(nt_env) : 0;
+    const int nt_force = g->tune.nt;   // (BLP_NT, read at handle creation)
     if (nt_force == 256 || nt_force == 512 || nt_force == 1024) nt = nt_force;
     else if (smem * 4 + 4096 <= budget) nt = 256;
     else if (smem * 2 + 2048 <= budget) nt = 512;
@@ -1115,6 +1128,9 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     size_t& occ_smem = g->occ_smem[nt_i][ranged ? 1 : 0][rec_mode ? 1 : 0];
 #define BLP_DISPATCH(NTV, RV)                                               \
     do {                                                                    \
+        rc = rec_mode ? raise_smem_optin<NTV, RV, true>(g->device, smem)    \
+                      : raise_smem_optin<NTV, RV, false>(g->device, smem);  \
+        if (rc != BLP_OK) break;                                            \
         if (occ_slot > 0 && occ_smem == smem) {                             \
             per_sm = occ_slot;                                              \
         } else {                                                            \
@@ -1139,8 +1155,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     // BLP_LIGHT_STREAM=0 keeps both on the caller's stream.
     bool light_aside = false;
     if (split) {
-        const char* ls = getenv("BLP_LIGHT_STREAM");
-        light_aside = g->side_stream != nullptr && !(ls && atoi(ls) == 0);
+        light_aside = g->side_stream != nullptr && g->tune.light_stream;
         if (light_aside) {
             BLP_TRY_SCRATCH(cudaEventRecord(g->ev_fork[side], st));
             BLP_TRY_SCRATCH(cudaStreamWaitEvent(g->side_stream, g->ev_fork[side], 0));

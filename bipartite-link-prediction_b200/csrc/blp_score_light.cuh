@@ -481,7 +481,7 @@ __global__ void k_hub_tables(const int* __restrict__ or_nodes, int n_bm,
     const unsigned long long row = m_row[or_nodes[o]];
     const int* adj = m_adj + row_first4(row) * 4;
     const unsigned* bm = hub_bm + (size_t)y * bm_words;
-    const int padded = ((row_deg(row) + 3) >> 2) << 2;   // rows are bank-striped: padding is interleaved
+    const int padded = ((row_deg(row) + 3) >> 2) << 2;   // padding sits at the row's tail; its bit is never on
     unsigned cnt = 0;
     unsigned long long acc = 0ull;
     for (int i = threadIdx.x; i < padded; i += blockDim.x) {

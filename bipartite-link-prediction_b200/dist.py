@@ -1,16 +1,41 @@
-"""Multi-GPU layer: shard the candidate pairs, replicate the adjacency, gather the results.
+"""Multi-GPU layer: shard the candidate pairs, replicate the adjacency, land the results on one rank.
 
 The reference is a single process; the only parallelism this path offers is
-over independent candidate pairs.  Every rank holds the whole graph (it is small next to
-180 GB of HBM), scores one contiguous slice of the pair list and the slices meet again in ONE
-final gather -- NCCL over NVLink on the GPU box, gloo in the CPU tests.  There is no collective
-inside the scoring itself.
+over independent candidate pairs.  Every rank (one process per GPU) holds the whole graph -- it is
+small next to 180 GB of HBM -- and scores one contiguous slice of the pair list.  There is no
+collective inside the scoring.
+
+How the slices meet again on rank `dst`:
+
+  * ``ResultWindow`` + ``score_sharded``  (the product path).  Rank `dst` owns ONE device buffer
+    holding every result column for the whole pair list and exposes it to its peers through CUDA
+    IPC (``blp_peer_alloc`` / ``blp_peer_open``).  Each rank hands addresses inside that window to
+    ``blp_score_pairs`` as its output pointers, so the scoring kernels' own epilogue stores carry
+    every row over NVLink / NVSwitch while the rest of the slice is still being scored: compute
+    and "gather" are one kernel, no SM runs a copy, no second pass over the results.
+  * ``gather_results``  (the baseline it is measured against, and what the gloo CPU test uses):
+    score into local memory, then move every column slice with one grouped batch of
+    point-to-point send / recv straight into place (NCCL over NVLink on the box).
 
 Slices are cut at user boundaries (no hop-2 set is built on two ranks for the user side) and
 balanced on an estimate of the work, not on the pair count: the streamed-list length deg(v) of
 every pair plus the two-hop expansion cost of every distinct user.
+One ``blp_score_pairs`` call takes fewer than 2^31 pairs, i.e. a rank's slice must stay below that
+(1 B pairs over 8 ranks = 125 M per rank).
 """
+import ctypes
+
 import numpy as np
+
+# the seven outputs the reference leaves on the host (similarity.py:61,106 + PA): 48 B per pair
+REFERENCE_COLUMNS = ('u_cn', 'u_jaccard', 'u_adamic', 'b_cn', 'b_jaccard', 'b_adamic', 'pa')
+# ... plus the two union sizes (not reference outputs; tests and the roofline use them): 56 B
+ALL_COLUMNS = REFERENCE_COLUMNS + ('u_union', 'b_union')
+_ITEMSIZE = {'cn': 4, 'union': 4, 'jaccard': 8, 'adamic': 8, 'pa': 8}
+
+
+def _kind(col):
+    return col if col == 'pa' else col[2:]
 
 
 def pair_costs(pair_u, pair_b, deg_u, deg_b, expansion_u=None):
@@ -57,14 +82,146 @@ def shard_pairs(pair_u, pair_b, rank, world, cost=None):
     return pair_u[lo:hi], pair_b[lo:hi], (lo, hi)
 
 
-def gather_results(local, counts, dst=0, group=None):
-    """Final gather of per-rank result columns to rank `dst`.
+# ------------------------------------------------------------------------------ the fused path
+class _DeviceMemory(object):
+    """A raw device range as something torch.as_tensor understands."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {'shape': (int(nbytes),), 'typestr': '|u1',
+                                         'data': (int(ptr), False), 'version': 2}
+
+
+class ResultWindow(object):
+    """The result table of a sharded scoring job: every column for all `n_total` pairs, resident
+    on rank `dst`, writable by the scoring kernels of every rank (see the module docstring).
+
+    Collective: every rank of `group` constructs it (the IPC handle is broadcast from `dst`).
+    ``columns`` selects what is kept; a column that is left out is not computed.
+    """
+
+    def __init__(self, graph, n_total, columns=REFERENCE_COLUMNS, dst=0, group=None):
+        import torch.distributed as dist
+        from . import _lib
+        self._lib = _lib.load()
+        self.device = graph.device
+        self.n_total = int(n_total)
+        self.columns = tuple(columns)
+        bad = [c for c in self.columns if c not in ALL_COLUMNS]
+        if bad:
+            raise ValueError('unknown result columns %r' % (bad,))
+        self.dst = dst
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.offsets, at = {}, 0
+        for c in self.columns:                      # struct of arrays, 256-byte aligned columns
+            self.offsets[c] = at
+            at += (_ITEMSIZE[_kind(c)] * max(self.n_total, 1) + 255) // 256 * 256
+        self.nbytes = max(at, 256)
+        self._base = ctypes.c_void_p()
+        self._owner = self.rank == dst
+        dev = self.device.index or 0
+        handle = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        if self._owner:
+            _lib.check(self._lib.blp_peer_alloc(dev, self.nbytes, ctypes.byref(self._base), handle),
+                       'blp_peer_alloc')
+        if self.world > 1:
+            box = [handle.raw if self._owner else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group else dst,
+                                       group=group)
+            if not self._owner:
+                _lib.check(self._lib.blp_peer_open(dev, box[0], ctypes.byref(self._base)),
+                           'blp_peer_open')
+        self.base = int(self._base.value)
+
+    def pointers(self, lo):
+        """Device addresses of row `lo` of every column, valid on THIS rank's device."""
+        return {c: self.base + self.offsets[c] + _ITEMSIZE[_kind(c)] * int(lo) for c in self.columns}
+
+    def bytes_per_pair(self):
+        return sum(_ITEMSIZE[_kind(c)] for c in self.columns)
+
+    def tensors(self):
+        """On `dst`: dict column -> torch tensor [n_total] viewing the window.  None elsewhere
+        (the peers only ever store into it from kernels)."""
+        if not self._owner:
+            return None
+        import torch
+        raw = torch.as_tensor(_DeviceMemory(self.base, self.nbytes), device=self.device)
+        dt = {'cn': torch.int32, 'union': torch.int32, 'jaccard': torch.float64,
+              'adamic': torch.float64, 'pa': torch.int64}
+        out = {}
+        for c in self.columns:
+            k = _kind(c)
+            out[c] = raw[self.offsets[c]:self.offsets[c] + _ITEMSIZE[k] * self.n_total].view(dt[k])
+        self._keepalive = raw
+        return out
+
+    def close(self):
+        if getattr(self, 'base', 0):
+            dev = self.device.index or 0
+            if self._owner:
+                self._lib.blp_peer_free(dev, self._base)
+            else:
+                self._lib.blp_peer_close(dev, self._base)
+            self.base = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def score_into_window(graph, d_u, d_b, window, lo, stream=None):
+    """Score the device-resident pairs (d_u, d_b) -- rows [lo, lo+n) of the job -- with the
+    window's columns as the kernels' output arrays.  Asynchronous on `stream`."""
+    from . import _lib
+    ptr = window.pointers(lo)
+    up = {(_kind(c)): p for c, p in ptr.items() if c.startswith('u_') or c == 'pa'}
+    bp = {(_kind(c)): p for c, p in ptr.items() if c.startswith('b_')}
+    if up:
+        graph.score_side(_lib.SIDE_USER, d_u, d_b, want=(), out_ptr=up, stream=stream)
+    if bp:
+        graph.score_side(_lib.SIDE_BUSINESS, d_u, d_b, want=(), out_ptr=bp, stream=stream)
+
+
+def score_sharded(graph, pair_u, pair_b, cost=None, dst=0, group=None, columns=REFERENCE_COLUMNS,
+                  window=None):
+    """Score this rank's slice of the (replicated) pair list on `graph`; the results of every rank
+    land in one window on `dst` through the kernels' own stores.
+
+    pair_u / pair_b are host int32 arrays holding the WHOLE pair list on every rank (grouped by
+    user).  Returns (dict column -> tensor over all pairs, window) on `dst`, (None, window)
+    elsewhere; keep the window alive as long as the tensors are used, close() it afterwards.
+    """
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    bounds = shard_bounds(pair_u, world, cost)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    if window is None:
+        window = ResultWindow(graph, len(pair_u), columns=columns, dst=dst, group=group)
+    with torch.cuda.device(graph.device):
+        du = torch.from_numpy(np.ascontiguousarray(pair_u[lo:hi], dtype=np.int32)).to(graph.device)
+        db = torch.from_numpy(np.ascontiguousarray(pair_b[lo:hi], dtype=np.int32)).to(graph.device)
+        if hi > lo:
+            score_into_window(graph, du, db, window, lo)
+        torch.cuda.synchronize(graph.device)     # this rank's rows have left for `dst`
+    if world > 1:
+        dist.barrier(group=group)                # ... and so have everybody else's
+    return window.tensors(), window
+
+
+# ------------------------------------------------------------------------------ baseline gather
+def gather_results(local, counts, dst=0, group=None, out=None):
+    """Final gather of per-rank result columns to rank `dst` with point-to-point transfers.
 
     local  : dict name -> 1-D torch tensor of this rank's slice (same names/dtypes on every rank)
     counts : list of slice lengths per rank (known to all ranks from shard_bounds)
-    Returns dict name -> concatenated tensor on `dst`, None elsewhere.  Slices are unequal, so
-    each column is padded to the longest slice for the collective and trimmed afterwards.
-    Works with the nccl backend (CUDA tensors, NVLink) and with gloo (CPU tensors, tests).
+    Returns dict name -> tensor over all pairs on `dst` (`out` may carry preallocated ones), None
+    elsewhere.  Slices are unequal, so every column slice is sent on its own, straight into its
+    place -- one grouped batch of send / recv (one ncclGroup on the nccl backend; gloo in tests).
     """
     import torch
     import torch.distributed as dist
@@ -72,109 +229,29 @@ def gather_results(local, counts, dst=0, group=None):
     rank = dist.get_rank(group)
     if len(counts) != world:
         raise ValueError('counts must list one slice length per rank')
-    longest = int(max(counts))
-    out = {} if rank == dst else None
-    for name in sorted(local):
-        t = local[name]
-        if t.numel() != counts[rank]:
+    names = sorted(local)
+    for name in names:
+        if local[name].numel() != counts[rank]:
             raise ValueError('%s: slice has %d entries, counts says %d' %
-                             (name, t.numel(), counts[rank]))
-        send = t
-        if t.numel() != longest:
-            send = torch.zeros(longest, dtype=t.dtype, device=t.device)
-            send[:t.numel()] = t
-        recv = None
-        if rank == dst:
-            recv = [torch.empty(longest, dtype=t.dtype, device=t.device) for _ in range(world)]
-        dist.gather(send.contiguous(), recv, dst=dst, group=group)
-        if rank == dst:
-            out[name] = torch.cat([recv[r][:counts[r]] for r in range(world)])
-    return out
-
-
-def score_sharded(graph, pair_u, pair_b, cost=None, dst=0, group=None):
-    """Score this rank's slice of the (replicated) pair list on `graph` and gather on `dst`.
-
-    pair_u / pair_b are host int32 arrays holding the WHOLE pair list on every rank (grouped by
-    user).  Returns the gathered dict of tensors on `dst` (caller order), None elsewhere.
-    """
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    bounds = shard_bounds(pair_u, world, cost)
-    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    du = torch.from_numpy(np.ascontiguousarray(pair_u[lo:hi], dtype=np.int32)).to(graph.device)
-    db = torch.from_numpy(np.ascontiguousarray(pair_b[lo:hi], dtype=np.int32)).to(graph.device)
-    local = graph.score_pairs(du, db)
-    counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
-    return gather_results(local, counts, dst=dst, group=group)
-
-
-def score_and_gather_overlapped(graph, d_u, d_b, chunks=4, dst=0, group=None, out=None, recv=None,
-                                reserve_sms=8):
-    """Score this rank's pairs in `chunks` slices and gather every slice on `dst` while the next
-    one is being scored (the gather rides a side stream; NCCL moves it over NVLink).
-
-    d_u / d_b: int32 CUDA tensors, the SAME length on every rank (pad with -1 if needed).
-    Returns (out, recv): this rank's result columns and, on `dst`, dict name -> [world, n] tensor.
-    `out` / `recv` from a previous call may be passed back in to reuse the buffers.
-    `reserve_sms` SMs are kept out of the persistent scoring grids for the duration of the call,
-    so that NCCL's send/receive kernels can run beside them.
-    """
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    n = d_u.numel()
-    dev = graph.device
-    main = torch.cuda.current_stream(dev)
-    if getattr(graph, '_comm_stream', None) is None:
-        graph._comm_stream = torch.cuda.Stream(device=dev)
-    comm = graph._comm_stream
-    dtypes = {'cn': torch.int32, 'union': torch.int32, 'jaccard': torch.float64,
-              'adamic': torch.float64}
-    keys = ['u_' + k for k in dtypes] + ['b_' + k for k in dtypes] + ['pa']
-    if out is None:
-        out = {k: torch.empty(n, dtype=dtypes.get(k[2:], torch.int64), device=dev) for k in keys}
-    if recv is None and rank == dst:
-        recv = {k: torch.empty((world, n), dtype=out[k].dtype, device=dev) for k in keys}
-    from . import _lib
-    chunks = max(1, min(int(chunks), n // 65536 or 1))
-    bounds = [(n * c) // chunks for c in range(chunks + 1)]
-    comm.wait_stream(main)
-    graph.reserve_sms(reserve_sms)
-
-    def gather_async(names, lo, hi, after):
-        ev = torch.cuda.Event()
-        ev.record(after)
-        with torch.cuda.stream(comm):
-            comm.wait_event(ev)
-            for k in names:
-                glist = [recv[k][r, lo:hi] for r in range(world)] if rank == dst else None
-                dist.gather(out[k][lo:hi], glist, dst=dst, group=group)
-
-    # business side once over all pairs (its hop-2 sets are shared by pairs of every slice), on a
-    # side stream so that it fills in beside the user-side slices ...
-    bkeys = [k for k in keys if k.startswith('b_')]
-    ukeys = [k for k in keys if not k.startswith('b_')]
-    if getattr(graph, '_side_stream', None) is None:
-        graph._side_stream = torch.cuda.Stream(device=dev)
-    side = graph._side_stream
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        graph.score_side(_lib.SIDE_BUSINESS, d_u, d_b, out={k[2:]: out[k] for k in bkeys},
-                         stream=side)
-    gather_async(bkeys, 0, n, side)      # queued first: it is the largest transfer
-    # ... and the user side slice by slice, each slice's gather behind the next slice's scoring
-    for c in range(chunks):
-        lo, hi = bounds[c], bounds[c + 1]
-        if hi <= lo:
-            continue
-        ou = {(k[2:] if k.startswith('u_') else k): out[k][lo:hi] for k in ukeys}
-        graph.score_side(_lib.SIDE_USER, d_u[lo:hi], d_b[lo:hi], want_pa=True, out=ou)
-        gather_async(ukeys, lo, hi, main)
-    main.wait_stream(side)
-    graph.reserve_sms(0)
-    main.wait_stream(comm)
-    return out, recv
+                             (name, local[name].numel(), counts[rank]))
+    starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    gdst = dist.get_global_rank(group, dst) if group is not None else dst
+    ops = []
+    if rank == dst:
+        if out is None:
+            out = {k: torch.empty(int(starts[-1]), dtype=local[k].dtype, device=local[k].device)
+                   for k in names}
+        for k in names:
+            out[k][int(starts[rank]):int(starts[rank + 1])].copy_(local[k])
+            for r in range(world):
+                if r != rank and counts[r] > 0:
+                    src = dist.get_global_rank(group, r) if group is not None else r
+                    ops.append(dist.P2POp(dist.irecv, out[k][int(starts[r]):int(starts[r + 1])], src,
+                                          group=group))
+    elif counts[rank] > 0:
+        for k in names:
+            ops.append(dist.P2POp(dist.isend, local[k].contiguous(), gdst, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out if rank == dst else None

@@ -9,6 +9,7 @@ scoring goes through ``score_pairs`` -> ``blp_score_pairs`` (CUDA, no CPU path).
 PyTorch is used here for device buffers and streams only.
 """
 import ctypes
+import time
 
 import numpy as np
 import torch
@@ -210,11 +211,13 @@ class BipartiteGraph(object):
 
     # ------------------------------------------------------------------ scoring
     def score_side(self, side, pair_u, pair_b, want=OUTPUTS_PER_SIDE, want_pa=False,
-                   want_hop2=False, out=None, stream=None):
+                   want_hop2=False, out=None, stream=None, out_ptr=None):
         """One ``blp_score_pairs`` call.  pair_u / pair_b: int32 CUDA tensors of local indices.
 
         Returns a dict of CUDA tensors (keys from ``want`` plus 'pa' / 'hop2' when asked).
-        ``out`` may carry preallocated tensors under the same keys.
+        ``out`` may carry preallocated tensors under the same keys.  ``out_ptr`` maps keys to raw
+        device addresses instead (n elements each, e.g. rows of a peer-mapped ``dist.ResultWindow``
+        on another GPU): those columns are written there and are not part of the returned dict.
         """
         if not (pair_u.is_cuda and pair_b.is_cuda):
             raise ValueError('pair_u / pair_b must be CUDA tensors (use score_pairs_host for '
@@ -230,8 +233,13 @@ class BipartiteGraph(object):
         dtypes = {'cn': torch.int32, 'union': torch.int32, 'jaccard': torch.float64,
                   'adamic': torch.float64, 'pa': torch.int64, 'hop2': torch.int32}
         keys = list(want) + (['pa'] if want_pa else []) + (['hop2'] if want_hop2 else [])
+        raw = dict(out_ptr or {})
+        if any(k not in dtypes for k in raw):
+            raise ValueError('out_ptr keys must be among %s' % sorted(dtypes))
         res = {}
         for k in keys:
+            if k in raw:
+                continue
             t = None if out is None else out.get(k)
             if t is None:
                 t = torch.empty(n, dtype=dtypes[k], device=self.device)
@@ -240,6 +248,8 @@ class BipartiteGraph(object):
             res[k] = t
 
         def ptr(k):
+            if k in raw:
+                return ctypes.c_void_p(int(raw[k]))
             return ctypes.c_void_p(res[k].data_ptr()) if k in res else None
 
         if stream is None:
@@ -345,9 +355,11 @@ class BipartiteGraph(object):
             host = {k: v.cpu().numpy() for k, v in res.items()}
         return host
 
-    def host_session(self, max_pairs):
-        """Reusable pinned/device buffers for repeated host-to-host scoring of <= max_pairs."""
-        return HostSession(self, max_pairs)
+    def host_session(self, max_pairs, columns=None):
+        """Reusable pinned/device buffers for repeated host-to-host scoring of <= max_pairs.
+        columns: None = the seven reference outputs (48 B per pair come back), 'all' = plus the
+        two union sizes (56 B), or an explicit tuple of column names."""
+        return HostSession(self, max_pairs, columns=columns)
 
     def score_id_pairs(self, ids_u, ids_b, want_hop2=False):
         """Same, for ids of the reference's shared id space (unknown ids score 0)."""
@@ -358,18 +370,30 @@ class BipartiteGraph(object):
 class HostSession(object):
     """End-to-end scoring with HOST buffers: page-locked pair and result arrays owned by the
     session, and ONE C-ABI call per step (`blp_score_pairs_host`) that uploads the ids, scores
-    both sides and copies the nine columns (56 B per pair) back, the copies overlapping the
-    kernels inside the library.  `score_pinned_py` drives the same pipeline from Python.
+    both sides and copies the result columns back, the copies overlapping the kernels inside the
+    library.  By default the columns are the seven outputs the reference leaves on the host
+    (similarity.py:61,106 + PA: 48 B per pair); the two union sizes are extra (``columns='all'``,
+    56 B) -- the link is the bottleneck of this call, so bytes that nobody reads stay on the device.
+    `score_pinned_py` drives the same pipeline from Python.
     """
 
-    KEYS = ('u_cn', 'u_union', 'u_jaccard', 'u_adamic', 'b_cn', 'b_union', 'b_jaccard',
-            'b_adamic', 'pa')
+    ALL_KEYS = ('u_cn', 'u_union', 'u_jaccard', 'u_adamic', 'b_cn', 'b_union', 'b_jaccard',
+                'b_adamic', 'pa')          # order of blp_score_pairs_host's output arguments
+    REFERENCE_KEYS = ('u_cn', 'u_jaccard', 'u_adamic', 'b_cn', 'b_jaccard', 'b_adamic', 'pa')
     DTYPES = {'cn': torch.int32, 'union': torch.int32, 'jaccard': torch.float64,
               'adamic': torch.float64, 'pa': torch.int64}
 
-    def __init__(self, graph, max_pairs):
+    def __init__(self, graph, max_pairs, columns=None):
         self.g, self.n_max = graph, int(max_pairs)
         n = self.n_max
+        if columns is None:
+            columns = self.REFERENCE_KEYS
+        elif columns == 'all':
+            columns = self.ALL_KEYS
+        bad = [c for c in columns if c not in self.ALL_KEYS]
+        if bad:
+            raise ValueError('unknown result columns %r' % (bad,))
+        self.KEYS = tuple(k for k in self.ALL_KEYS if k in columns)
         self.h_u = torch.empty(n, dtype=torch.int32).pin_memory()
         self.h_b = torch.empty(n, dtype=torch.int32).pin_memory()
         self.h_out = {}
@@ -378,6 +402,32 @@ class HostSession(object):
         self.d_out = None          # device staging of score_pinned_py, made on first use
         self.h2d_bytes_per_pair = 8
         self.d2h_bytes_per_pair = sum(self.h_out[k].element_size() for k in self.KEYS)
+
+    def measure_link(self, n, reps=3):
+        """The host link under this session's own buffers: pinned D2H of the result columns and
+        H2D of the pair ids, timed alone.  The copy-back time is the floor under one step."""
+        n = min(int(n), self.n_max)
+        dev = self.g.device
+        with torch.cuda.device(dev):
+            d = {k: torch.empty(n, dtype=self.h_out[k].dtype, device=dev) for k in self.KEYS}
+            du = torch.empty(n, dtype=torch.int32, device=dev)
+            best_d2h = best_h2d = float('inf')
+            for _ in range(reps):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                for k in self.KEYS:
+                    self.h_out[k][:n].copy_(d[k], non_blocking=True)
+                torch.cuda.synchronize(dev)
+                best_d2h = min(best_d2h, time.perf_counter() - t0)
+                t0 = time.perf_counter()
+                du.copy_(self.h_u[:n], non_blocking=True)
+                torch.cuda.synchronize(dev)
+                best_h2d = min(best_h2d, time.perf_counter() - t0)
+        d2h_bytes = self.d2h_bytes_per_pair * n
+        return {'d2h_gbs': d2h_bytes / best_d2h / 1e9, 'h2d_gbs': 4 * n / best_h2d / 1e9,
+                'd2h_floor_ms': best_d2h * 1e3,
+                'what': 'pinned copies timed alone on this box; d2h_floor_ms = the %d result bytes '
+                        'of one step at that rate' % d2h_bytes}
 
     def _device_staging(self):
         if self.d_out is None:
@@ -410,7 +460,7 @@ class HostSession(object):
         if n > self.n_max:
             raise ValueError('pair count %d exceeds the session capacity %d' % (n, self.n_max))
         lib = self.g._lib
-        outs = [self.h_out[k].data_ptr() for k in self.KEYS]
+        outs = [self.h_out[k].data_ptr() if k in self.h_out else None for k in self.ALL_KEYS]
         _lib.check(lib.blp_score_pairs_host(self.g._h, self.h_u.data_ptr(), self.h_b.data_ptr(), n,
                                             *outs, int(user_chunks), int(lead_chunks),
                                             int(biz_chunks)), 'blp_score_pairs_host')

@@ -16,6 +16,8 @@
  *     reference's shared id space onto them).  In a pair, an index that is negative, out of range
  *     or names a node of degree 0 means "id not in graph": every output of that pair is 0
  *     (similarity.py:59-60, 104-105).
+ *   - Every entry point runs on its handle's device and restores the caller's current device
+ *     before it returns.
  *   - A handle's graph is immutable after creation.  Scoring calls issued by ONE host thread on
  *     several streams overlap on the device; concurrent calls from several host threads on the
  *     same handle are not supported (the handle owns a side stream, events and the accounting
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define BLP_VERSION 100 /* major*10000 + minor*100 + patch */
+#define BLP_VERSION 200 /* major*10000 + minor*100 + patch */
 
 typedef enum blp_status {
     BLP_OK = 0,
@@ -194,6 +196,25 @@ int blp_eval_roc_auc(const int32_t* labels, const double* scores, int64_t n,
  * (NCCL's send/receive kernels need somewhere to run) reserves a few.
  */
 int blp_graph_reserve_sms(blp_graph* g, int n_sms);
+
+/*
+ * Peer windows -- the final gather of the multi-GPU path (the reference is a
+ * single process and has no counterpart) without a collective.  The destination rank allocates one
+ * device buffer and exports it; every other rank (ONE PROCESS PER GPU: a handle cannot be opened
+ * by the process that exported it) maps it and passes addresses inside it as the output pointers
+ * of blp_score_pairs, so the scoring kernels' epilogue stores carry every result over
+ * NVLink / NVSwitch as it is produced.  The rows are complete on the owner once the writers'
+ * streams have been synchronised (then signal the owner, e.g. with a barrier).
+ *   blp_peer_alloc : cudaMalloc `bytes` on `device`, handle_out = BLP_IPC_HANDLE_BYTES opaque bytes
+ *                    to hand to the other ranks (torch.distributed, a pipe, a file ...)
+ *   blp_peer_open  : map an exported buffer for kernels running on `device`; enables peer access
+ *   blp_peer_close / blp_peer_free : undo open / alloc (both wait for the device to go idle)
+ */
+#define BLP_IPC_HANDLE_BYTES 64
+int blp_peer_alloc(int device, int64_t bytes, void** dev_ptr, unsigned char* handle_out);
+int blp_peer_open(int device, const unsigned char* handle, void** dev_ptr);
+int blp_peer_close(int device, void* dev_ptr);
+int blp_peer_free(int device, void* dev_ptr);
 
 /* Accounting of the most recent blp_score_pairs on this handle (per side; with
  * blp_score_pairs_host: of the last slice).  The two event times

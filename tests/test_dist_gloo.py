@@ -1,7 +1,8 @@
 """World-size-2 gloo test of the N>1 path on CPU: shard -> score -> final gather == unsharded.
 
 The scorer stand-in on CPU is the C oracle (tests may use it); on the GPU box the same
-`shard_bounds` / `gather_results` run under NCCL in bench.py and in test_gpu_multi.py.
+`shard_bounds` / `gather_results` run under NCCL -- and `score_sharded` with its peer-memory
+result window -- in tests/test_gpu_multi.py (torchrun, one process per GPU) and in bench.py --gpus N.
 """
 import os
 import socket
@@ -65,4 +66,4 @@ def test_shard_score_gather_world2():
         assert p.exitcode == 0
     status, counts = q.get(timeout=10)
     assert status == 'ok'
-    assert sum(counts) == 6000 and min(counts) > 0 and counts[0] != counts[1] or counts[0] == counts[1]
+    assert sum(counts) == 6000 and min(counts) > 0

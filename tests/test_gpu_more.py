@@ -141,7 +141,7 @@ def test_host_session_matches_plain_path(mods):
     pu, pv = pu[perm], pv[perm]
     G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
     want = G.score_pairs_host(pu, pv)
-    sess = G.host_session(pu.size + 10)
+    sess = G.host_session(pu.size + 10, columns='all')
     for chunks, lead in ((1, 0), (1, 1), (4, 0), (8, 1), (8, 3), (16, 20)):
         hu, hb = sess.pinned_inputs(pu.size)
         hu[:] = pu
@@ -152,6 +152,13 @@ def test_host_session_matches_plain_path(mods):
     got = sess.score(pu[:777], pv[:777])
     for k in want:
         assert np.array_equal(got[k], want[k][:777]), k
+    # the default session brings back the seven reference outputs only (48 B per pair)
+    lean = G.host_session(pu.size)
+    assert lean.d2h_bytes_per_pair == 48 and 'u_union' not in lean.KEYS
+    got = lean.score(pu, pv)
+    assert set(got) == set(lean.REFERENCE_KEYS)
+    for k in got:
+        assert np.array_equal(got[k], want[k]), k
 
 
 def test_hub_bitmaps_do_not_change_results(mods, monkeypatch):
@@ -170,7 +177,8 @@ def test_hub_bitmaps_do_not_change_results(mods, monkeypatch):
 
 
 def test_id_range_passes_do_not_change_results(mods, monkeypatch):
-    """Bitmap cut into id ranges (several passes per group) vs one pass: bit-identical."""
+    """Bitmap cut into id ranges (several passes per group) vs one pass: bit-identical.
+    (BLP_RANGES is read when a handle is created.)"""
     graph, synth = mods
     lib = pkg('_lib')
     cfg, eu, eb, pu, pv = synth.make_config('C1', n_pairs=30_000)
@@ -179,10 +187,40 @@ def test_id_range_passes_do_not_change_results(mods, monkeypatch):
     assert G.score_stats(lib.SIDE_USER)['range_passes'] == 1
     for r in ('2', '5'):
         monkeypatch.setenv('BLP_RANGES', r)
-        many = G.score_pairs_host(pu, pv, want_hop2=True)
-        assert G.score_stats(lib.SIDE_USER)['range_passes'] == int(r)
+        G2 = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+        many = G2.score_pairs_host(pu, pv, want_hop2=True)
+        assert G2.score_stats(lib.SIDE_USER)['range_passes'] == int(r)
         for k in one:
             assert np.array_equal(one[k], many[k]), (r, k)
+    monkeypatch.delenv('BLP_RANGES')
+    again = G.score_pairs_host(pu, pv, want_hop2=True)      # the first handle never saw the variable
+    assert G.score_stats(lib.SIDE_USER)['range_passes'] == 1
+    for k in one:
+        assert np.array_equal(one[k], again[k]), k
+
+
+def test_interleaved_handles_of_different_size(mods):
+    """Two handles on one device whose bitmaps differ in size (a train and a test graph): scoring
+    big, small, big again must work -- the shared-memory opt-in is per kernel and process, not
+    per handle, and is only ever raised."""
+    import torch
+    from oracle import c_oracle
+    graph, synth = mods
+    big = (200_000, 3000, 300_000)
+    small = (5_000, 3000, 20_000)
+    built = []
+    for (nu, nb, nr), seed in ((big, 31), (small, 32)):
+        eu, eb = synth.make_graph(nu, nb, nr, seed=seed, shift_u=5.0, shift_b=5.0)
+        pu, pv = synth.make_pairs(nu, nb, eu, eb, 8000, k=8, seed=seed + 1)
+        G = graph.BipartiteGraph(nu, nb, eu, eb)
+        built.append((G, nu, nb, eu, eb, pu, pv))
+    prev = torch.cuda.current_device()
+    for which in (0, 1, 0, 1, 0):
+        G, nu, nb, eu, eb, pu, pv = built[which]
+        got = G.score_pairs_host(pu, pv)
+        want = c_oracle.score_pair_arrays(nu, nb, eu, eb, pu, pv)
+        check_against(got, want, pu.size)
+    assert torch.cuda.current_device() == prev      # entry points restore the caller's device
 
 
 def test_universe_larger_than_shared_memory(mods):

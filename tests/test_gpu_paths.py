@@ -139,7 +139,7 @@ def test_host_buffer_entry_point(mods):
     G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
     want = G.score_pairs_host(pu, pv)            # device call + explicit copies
     n = pu.size
-    sess = G.host_session(n)
+    sess = G.host_session(n, columns='all')
     for plan in ((0, -1, 0), (1, 0, 1), (3, 2, 1), (7, 1, 4)):
         got = sess.score(pu, pv) if plan == (0, -1, 0) else None
         if got is None:
@@ -155,7 +155,7 @@ def test_host_buffer_entry_point(mods):
     rc = G._lib.blp_score_pairs_host(G._h, pu_c.ctypes.data, pv_c.ctypes.data, n,
                                      *[c.ctypes.data for c in cols], 0, -1, 0)
     assert rc == lib_mod.BLP_OK
-    for k, c in zip(sess.KEYS, cols):
+    for k, c in zip(sess.ALL_KEYS, cols):
         assert np.array_equal(c, want[k]), k
     # a NULL column is skipped (not copied back); no column at all is refused; n = 0 is a no-op
     some = [c.ctypes.data for c in cols]
