@@ -49,6 +49,7 @@ namespace blp {
 struct TileSmem {
     unsigned long long row[kTile];     // packed row descriptor of every list of the tile
     unsigned long long aa[kTile];      // Q24.40 Adamic-Adar accumulators
+    unsigned long long hub_bar;        // mbarrier the TMA bulk copy of a hub bitmap completes on
     int scan[kTile + 8];               // exclusive prefix of long-list chunk counts, [kTile] = total
     int coarse[32];                    // scan[8*i], contiguous: conflict-free first probe
     int next_chunk[4];                 // dynamic chunk dispensers, one per sweep kind (OP_*)
@@ -218,7 +219,8 @@ __device__ __forceinline__ void touch4(unsigned* bm, int4 v, uint4 wt, unsigned&
 // 512-id chunks dealt round-robin to warps, so a hub list is spread over the whole CTA.
 template <int NT, int OP, bool RANGED>
 __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, TileSmem& ts,
-                                               int count, int lane, int warp, int lo, int self) {
+                                               int count, int lane, int warp, int lo, int self,
+                                               unsigned long long pol) {
     unsigned set_total = 0;   // OP_SET: bits this thread turned on
     TileSmem* const list = (OP == OP_SET && !RANGED && ts.list_on) ? &ts : nullptr;
     constexpr int NW = NT / 32;
@@ -240,8 +242,8 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
             unsigned long long acc = 0ull;
             if (mine) {
                 const long long at = row_first4(row) + sub;
-                int4 v = ldg_stream(adj4 + at);
-                uint4 wt = OP == OP_TEST ? ldg_stream_u(adjw4 + at) : zero4;
+                int4 v = ldg_stream(adj4 + at, pol);
+                uint4 wt = OP == OP_TEST ? ldg_stream_u(adjw4 + at, pol) : zero4;
                 touch4<OP, RANGED>(bm, v, wt, cnt, acc, a.n_side, lo, a.range_bits, list, self);
             }
             if (OP == OP_SET) set_total += cnt;
@@ -277,12 +279,12 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
                     for (int k = 0; k < 4; ++k)   // bit n_side is never on in a hub bitmap
                         w[k] = i0 + 32 * k < nl ? ts.hub[i0 + 32 * k] : a.n_side;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) word[k] = __ldg(hb + (w[k] >> 5));
+                    for (int k = 0; k < 4; ++k) word[k] = ldg_keep(hb + (w[k] >> 5), pol);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if ((word[k] >> (w[k] & 31)) & 1u) {
                             ++cnt;
-                            acc += __ldg(a.node_wt + w[k]);
+                            acc += ldg_keep(a.node_wt + w[k], pol);
                         }
                 }
                 cnt = __reduce_add_sync(kFull, cnt);
@@ -325,8 +327,8 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const int i = lane + 32 * (2 * half + k);
-                    v[k] = i < n ? ldg_stream(adj4 + at + i) : sent4;
-                    wt[k] = (OP == OP_TEST && i < n) ? ldg_stream_u(adjw4 + at + i) : zero4;
+                    v[k] = i < n ? ldg_stream(adj4 + at + i, pol) : sent4;
+                    wt[k] = (OP == OP_TEST && i < n) ? ldg_stream_u(adjw4 + at + i, pol) : zero4;
                 }
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
@@ -382,6 +384,9 @@ __device__ unsigned long long g_phase_cycles[16];
 #ifndef BLP_THREADS_PER_SM
 #define BLP_THREADS_PER_SM 1024
 #endif
+#ifndef BLP_HUB_TMA
+#define BLP_HUB_TMA 1   // 0: A/B build with the cp.async hub copy
+#endif
 
 // Descriptor of one work item (group) as the kernel carries it in registers.  The uniform part
 // of the chain  item -> node -> (pair range, row)  is fetched for the NEXT group in two stages
@@ -432,11 +437,14 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
     if (*a.mode == MODE_RUNS) {   // kernel parameters are per-thread copies: patch them locally
         a.pg = nullptr;
     }
+    const unsigned long long pol = l2_keep_policy();
+    unsigned hub_phase = 0;   // parity of ts.hub_bar's current phase (uniform across the CTA)
 
 #ifdef BLP_PHASE_TIMING
     long long t_last = clock64();
 #endif
     if (tid == 0) {
+        mbar_init(&ts.hub_bar, 1);
         ts.item_next = atomicAdd(a.work_counter, 1);
         ts.nhub = 0;
         ts.hop2cnt = 0;
@@ -449,6 +457,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         const int n4 = a.bm_words >> 2;
         for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+    fence_async_smem();   // the clear (and the barrier's init) before any bulk copy into the bitmap
     __syncthreads();
     GroupRegs cur;
     cur.item = ts.item_next;
@@ -471,15 +480,17 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             for (long long k = p0 + tid; k < p1; k += NT) {
                 int idx = a.pg ? a.pg[k].x : (int)k;
                 if (REC) {
-                    a.rec[3 * k] = a.rec[3 * k + 1] = a.rec[3 * k + 2] = 0ull;
+                    st_stream(a.rec + 3 * k, 0ull);
+                    st_stream(a.rec + 3 * k + 1, 0ull);
+                    st_stream(a.rec + 3 * k + 2, 0ull);
                 } else {
-                    if (a.cn) a.cn[idx] = 0;
-                    if (a.uni) a.uni[idx] = 0;
-                    if (a.jac) a.jac[idx] = 0.0;
-                    if (a.aa) a.aa[idx] = 0.0;
+                    if (a.cn) st_stream(a.cn + idx, 0);
+                    if (a.uni) st_stream(a.uni + idx, 0);
+                    if (a.jac) st_stream(a.jac + idx, 0.0);
+                    if (a.aa) st_stream(a.aa + idx, 0.0);
                 }
-                if (a.pa) a.pa[idx] = 0;
-                if (a.hop2) a.hop2[idx] = 0;
+                if (a.pa) st_stream(a.pa + idx, 0ll);
+                if (a.hop2) st_stream(a.hop2 + idx, 0);
             }
             __syncthreads();                       // everyone is past reading ts.item_next
             if (tid == 0) ts.item_next = claimed;
@@ -555,23 +566,35 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 if (nhub == 0) {
                     // nothing to OR, and no barrier needed before the list walk
                 } else if (tb == 0 && !RANGED) {
-                    // first hub of the first tile: asynchronous 16-byte copies straight into the
-                    // (not yet initialised) bitmap -- every copy of the thread is in flight at
-                    // once and no register holds data; it turns on exactly deg(hub) bits
+                    // first hub of the first tile: ONE TMA bulk copy (cp.async.bulk, UBLKCP) of the
+                    // hub's whole bitmap straight over the (all-zero) shared bitmap, issued by one
+                    // thread and completing on an mbarrier -- no thread spends issue slots or
+                    // registers on the 46 KB, and it turns on exactly deg(hub) bits.  The clear
+                    // that precedes it was fenced for the async proxy where it was written.
+#if BLP_HUB_TMA
+                    if (tid == 0) {
+                        const unsigned bytes = (unsigned)a.bm_words * 4u;
+                        mbar_expect_tx(&ts.hub_bar, bytes);
+                        bulk_copy_g2s(bm, h4 + (size_t)ts.hub[0] * hub4, bytes, &ts.hub_bar);
+                        newbits += ts.cn[0];
+                    }
+                    first_reg = 1;
+                    mbar_wait(&ts.hub_bar, hub_phase);   // every thread: the bytes have landed
+                    hub_phase ^= 1u;
+#else
+                    // (A/B build: the Ampere-style copy, 16 bytes per cp.async, every thread issuing)
                     const uint4* src = h4 + (size_t)ts.hub[0] * hub4;
                     for (int i = tid; i < n4; i += NT) {
                         const unsigned dst = (unsigned)__cvta_generic_to_shared(b4 + i);
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst),
-                                     "l"(src + i)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + i)
                                      : "memory");
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
                     if (tid == 0) newbits += ts.cn[0];
                     first_reg = 1;
-                    if (nhub > 1) {
-                        asm volatile("cp.async.wait_group 0;" ::: "memory");
-                        // own words only: no barrier needed before OR-ing further hubs into them
-                    }
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    (void)hub_phase;
+#endif
                 }
                 if (nhub > first_reg) {
                     const bool fresh = false;   // words are valid (zero or earlier hubs / tiles)
@@ -585,9 +608,9 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                                    __popc(acc1.x) + __popc(acc1.y) + __popc(acc1.z) + __popc(acc1.w);
                         for (int h = first_reg; h < nhub; ++h) {
                             const uint4* src = h4 + (size_t)ts.hub[h] * hub4 + lo4;
-                            const uint4 q0 = lo4 + i0 < hub4 ? __ldg(src + i0)
+                            const uint4 q0 = lo4 + i0 < hub4 ? ldg_keep(src + i0, pol)
                                                              : make_uint4(0u, 0u, 0u, 0u);
-                            const uint4 q1 = (ok1 && lo4 + i1 < hub4) ? __ldg(src + i1)
+                            const uint4 q1 = (ok1 && lo4 + i1 < hub4) ? ldg_keep(src + i1, pol)
                                                                       : make_uint4(0u, 0u, 0u, 0u);
                             acc0.x |= q0.x;
                             acc0.y |= q0.y;
@@ -604,7 +627,6 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                         if (ok1) b4[i1] = acc1;
                     }
                 }
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
             if (pass == 0 && tb == 0 && tid < kTile) {
                 // ts.idx / ts.aa are idle until phase 3: the first pair tile waits there
@@ -617,7 +639,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             }
             if (pass == 0 && tb == 0) stage2(a, nxt);
             BLP_TICK(2);
-            newbits += (int)sweep_tile<NT, OP_SET, RANGED>(a, bm, ts, count, lane, warp, lo, x);
+            newbits += (int)sweep_tile<NT, OP_SET, RANGED>(a, bm, ts, count, lane, warp, lo, x, pol);
             newbits = __reduce_add_sync(kFull, newbits);
             if (lane == 0 && newbits != 0) atomicAdd(&ts.hop2cnt, newbits);
             __syncthreads();
@@ -661,7 +683,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             tile_scan<NT>(ts, nch, tid, count);
             if (pass == 0 && tb == p0) stage4(a, nxt);
             BLP_TICK(6);
-            sweep_tile<NT, OP_TEST, RANGED>(a, bm, ts, count, lane, warp, lo, x);
+            sweep_tile<NT, OP_TEST, RANGED>(a, bm, ts, count, lane, warp, lo, x, pol);
             __syncthreads();
             if (!RANGED && tid == 0) ts.nprobe = 0;   // next use is behind the barrier below
             BLP_TICK(7);
@@ -686,19 +708,20 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                 int u = hop2 + pdeg - c;   // |a| + |b| - |a & b|  (similarity.py:110)
                 const double jv = __ddiv_rn((double)c, (double)u);
                 const double av = (double)ts.aa[tid] * (1.0 / (double)(1ull << BLP_AA_FRAC_BITS));
+                // results stream out once (on the multi-GPU path into a peer's memory): evict-first
                 if (REC) {
                     unsigned long long* r = a.rec + 3 * (tb + tid);
-                    r[0] = (unsigned long long)(unsigned)c | ((unsigned long long)(unsigned)u << 32);
-                    r[1] = (unsigned long long)__double_as_longlong(jv);
-                    r[2] = (unsigned long long)__double_as_longlong(av);
+                    st_stream(r, (unsigned long long)(unsigned)c | ((unsigned long long)(unsigned)u << 32));
+                    st_stream(r + 1, (unsigned long long)__double_as_longlong(jv));
+                    st_stream(r + 2, (unsigned long long)__double_as_longlong(av));
                 } else {
-                    if (a.cn) a.cn[idx] = c;
-                    if (a.uni) a.uni[idx] = u;
-                    if (a.jac) a.jac[idx] = jv;
-                    if (a.aa) a.aa[idx] = av;
+                    if (a.cn) st_stream(a.cn + idx, c);
+                    if (a.uni) st_stream(a.uni + idx, u);
+                    if (a.jac) st_stream(a.jac + idx, jv);
+                    if (a.aa) st_stream(a.aa + idx, av);
                 }
-                if (a.pa) a.pa[idx] = (long long)xdeg * (long long)pdeg;
-                if (a.hop2) a.hop2[idx] = hop2;
+                if (a.pa) st_stream(a.pa + idx, (long long)xdeg * (long long)pdeg);
+                if (a.hop2) st_stream(a.hop2 + idx, hop2);
             }
             __syncthreads();
             BLP_TICK(8);
@@ -708,6 +731,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             uint4* b4 = reinterpret_cast<uint4*>(bm);
             const int n4 = a.bm_words >> 2;
             for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+            fence_async_smem();   // ... before the next group's bulk copy may land on these words
         }
         }   // id-range passes
         if (tid == 0) {   // ordered before the next group's counting by its barriers

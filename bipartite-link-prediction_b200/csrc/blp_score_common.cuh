@@ -76,11 +76,34 @@ struct SideArgs {
     int* hop2;
 };
 
-__device__ __forceinline__ int4 ldg_stream(const int4* p) {
+// ---- L2 residency hints -------------------------------------------------------------------
+// The graph (adjacency, weights, hub bitmaps, row descriptors) is what every group re-reads; the
+// pair ids, the per-call scratch and the result columns stream through once.  Graph loads carry an
+// L2 evict_last policy, the streams use evict-first loads / stores (ld/st.global.cs), so that the
+// 0.5 GB of results per step do not push the graph out of L2 (BLP_L2_HINTS=0 compiles both away).
+#ifndef BLP_L2_HINTS
+#define BLP_L2_HINTS 1
+#endif
+
+__device__ __forceinline__ unsigned long long l2_keep_policy() {
+    unsigned long long pol = 0ull;
+#if BLP_L2_HINTS
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    return pol;
+}
+
+__device__ __forceinline__ int4 ldg_stream(const int4* p, unsigned long long pol) {
     int4 r;
+#if BLP_L2_HINTS
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
+#endif
     return r;
 }
 
@@ -94,12 +117,94 @@ __device__ __forceinline__ int row_slot1(unsigned long long row) {
     return (int)((row >> BLP_ROW_SLOT_SHIFT) & (unsigned long long)BLP_ROW_MAX_SLOTS);
 }
 
-__device__ __forceinline__ uint4 ldg_stream_u(const uint4* p) {
+__device__ __forceinline__ uint4 ldg_stream_u(const uint4* p, unsigned long long pol) {
     uint4 r;
+#if BLP_L2_HINTS
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
+#endif
     return r;
+}
+
+// graph data through the read-only path with the keep-in-L2 policy (L1 allocation as usual)
+__device__ __forceinline__ uint4 ldg_keep(const uint4* p, unsigned long long pol) {
+#if BLP_L2_HINTS
+    uint4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ unsigned ldg_keep(const unsigned* p, unsigned long long pol) {
+#if BLP_L2_HINTS
+    unsigned r;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
+
+// streaming (evict-first) accessors for data that passes through once
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, T v) {
+#if BLP_L2_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+template <typename T>
+__device__ __forceinline__ T ld_once(const T* p) {
+#if BLP_L2_HINTS
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+
+// ---- TMA bulk copy + mbarrier (sm_90+; the hub-bitmap copy of k_score_side) --------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make generic-proxy shared-memory writes (and the barrier's init) visible to the async proxy
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// one thread: global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; the copy
+// engine signals `bar` with the byte count when the data has landed
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, unsigned bytes,
+                                              unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "BLP_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BLP_MBAR_DONE;\n"
+        "bra BLP_MBAR_WAIT;\n"
+        "BLP_MBAR_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
 }
 
 // grouping mode, decided on the device (blp_score_group.cuh)
@@ -107,7 +212,7 @@ enum { MODE_SORT = 0, MODE_RUNS = 1 };
 
 // (caller-order index, partner) of the pair at grouped position k
 __device__ __forceinline__ int2 pair_at(const SideArgs& a, long long k) {
-    return a.pg ? a.pg[k] : make_int2((int)k, a.caller_y[k]);
+    return a.pg ? ld_once(a.pg + k) : make_int2((int)k, ld_once(a.caller_y + k));
 }
 
 constexpr int kShortV4 = 4;   // lists of <= 16 ids take the sub-warp path (4 lanes per list)

@@ -222,12 +222,12 @@ __global__ void k_unpermute(const int* __restrict__ mode, const unsigned long lo
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const unsigned long long* r = rec + 3ll * inv[i];
-        const unsigned long long c = r[0];
-        if (cn) cn[i] = (int)(unsigned)c;
-        if (uni) uni[i] = (int)(unsigned)(c >> 32);
-        if (jac) jac[i] = __longlong_as_double((long long)r[1]);
-        if (aa) aa[i] = __longlong_as_double((long long)r[2]);
+        const unsigned long long* r = rec + 3ll * ld_once(inv + i);
+        const unsigned long long c = ld_once(r);
+        if (cn) st_stream(cn + i, (int)(unsigned)c);
+        if (uni) st_stream(uni + i, (int)(unsigned)(c >> 32));
+        if (jac) st_stream(jac + i, __longlong_as_double((long long)ld_once(r + 1)));
+        if (aa) st_stream(aa + i, __longlong_as_double((long long)ld_once(r + 2)));
     }
 }
 

@@ -87,14 +87,15 @@ __device__ __forceinline__ bool light_insert(int* table, int id) {
 
 // expansion step for the four ids of one 128-bit load; new ids are appended to the list with one
 // ballot per component (list_n is warp-uniform)
-__device__ __forceinline__ bool hub_bit(const unsigned* hbm, int id) {
-    return (__ldg(hbm + (id >> 5)) >> (id & 31)) & 1u;
+__device__ __forceinline__ bool hub_bit(const unsigned* hbm, int id, unsigned long long pol) {
+    return (ldg_keep(hbm + (id >> 5), pol) >> (id & 31)) & 1u;
 }
 
 // hbm: bitmap of the group's single hub (null = none); ids already in it stay out of the table
 template <int SLOTS>
 __device__ __forceinline__ void light_expand4(int* table, int* list, int4 v, bool active, int x,
-                                              int n_side, const unsigned* hbm, int& list_n, int lane) {
+                                              int n_side, const unsigned* hbm, int& list_n, int lane,
+                                              unsigned long long pol) {
     const int id[4] = {v.x, v.y, v.z, v.w};
     bool want[4];
 #pragma unroll
@@ -102,7 +103,7 @@ __device__ __forceinline__ void light_expand4(int* table, int* list, int4 v, boo
     if (hbm) {
         bool in_hub[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) in_hub[k] = want[k] && hub_bit(hbm, id[k]);   // four loads in flight
+        for (int k = 0; k < 4; ++k) in_hub[k] = want[k] && hub_bit(hbm, id[k], pol);   // four loads in flight
 #pragma unroll
         for (int k = 0; k < 4; ++k) want[k] = want[k] && !in_hub[k];
     }
@@ -118,7 +119,7 @@ __device__ __forceinline__ void light_expand4(int* table, int* list, int4 v, boo
 template <int SLOTS>
 __device__ __forceinline__ void light_test4(const int* table, int4 v, uint4 wt, int x,
                                             const unsigned* hbm, unsigned& cnt,
-                                            unsigned long long& acc) {
+                                            unsigned long long& acc, unsigned long long pol) {
     const int id[4] = {v.x, v.y, v.z, v.w};
     const unsigned w[4] = {wt.x, wt.y, wt.z, wt.w};
     bool hit[4];
@@ -127,7 +128,7 @@ __device__ __forceinline__ void light_test4(const int* table, int4 v, uint4 wt, 
     if (hbm) {   // hop2(x) also holds N(h) \ {x}; bit n_side (the padding id) is never on
         bool in_hub[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) in_hub[k] = !hit[k] && id[k] != x && hub_bit(hbm, id[k]);
+        for (int k = 0; k < 4; ++k) in_hub[k] = !hit[k] && id[k] != x && hub_bit(hbm, id[k], pol);
 #pragma unroll
         for (int k = 0; k < 4; ++k) hit[k] = hit[k] || in_hub[k];
     }
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLP_LIGHT_MIN_CTAS) k_score_light(
     Smem& ls = reinterpret_cast<Smem*>(smem_raw)[warp];
     const int n_items = *a.n_items;
     if (*a.mode == MODE_RUNS) a.pg = nullptr;
+    const unsigned long long pol = l2_keep_policy();
     const int4* adj4 = reinterpret_cast<const int4*>(a.m_adj);
     const uint4* adjw4 = reinterpret_cast<const uint4*>(a.m_adjw);
     const int4 sent4 = make_int4(a.n_side, a.n_side, a.n_side, a.n_side);
@@ -271,13 +273,13 @@ __global__ void __launch_bounds__(WARPS * 32, BLP_LIGHT_MIN_CTAS) k_score_light(
                     const int j = seg_search(incl, ii);
                     const int off = ii - __shfl_sync(kFull, excl, j);
                     const long long at = __shfl_sync(kFull, mat, j) + off;
-                    v[h] = ok[h] ? ldg_stream(adj4 + at) : sent4;
+                    v[h] = ok[h] ? ldg_stream(adj4 + at, pol) : sent4;
                 }
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
                     if (i0 + 32 * h < total)
                         light_expand4<SLOTS>(ls.table, ls.list, v[h], ok[h], x, a.n_side, hbm, list_n,
-                                             lane);
+                                             lane, pol);
             }
         }
         __syncwarp();
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLP_LIGHT_MIN_CTAS) k_score_light(
                     const bool x_in = __any_sync(kFull, cur.m == yj);   // y in N(x)
                     if (x_in && lane == 0) {
                         cnt -= 1u;
-                        acc -= (unsigned long long)__ldg(a.node_wt + x);
+                        acc -= (unsigned long long)ldg_keep(a.node_wt + x, pol);
                     }
                 }
                 for (int i0 = lane; i0 < list_n; i0 += 128) {
@@ -335,12 +337,12 @@ __global__ void __launch_bounds__(WARPS * 32, BLP_LIGHT_MIN_CTAS) k_score_light(
                     for (int k = 0; k < 4; ++k)   // bit n_side is never on in a hub bitmap
                         w[k] = i0 + 32 * k < list_n ? ls.list[i0 + 32 * k] : a.n_side;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) word[k] = __ldg(hb + (w[k] >> 5));
+                    for (int k = 0; k < 4; ++k) word[k] = ldg_keep(hb + (w[k] >> 5), pol);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         if ((word[k] >> (w[k] & 31)) & 1u) {
                             ++cnt;
-                            acc += __ldg(a.node_wt + w[k]);
+                            acc += ldg_keep(a.node_wt + w[k], pol);
                         }
                 }
                 cnt = __reduce_add_sync(kFull, cnt);
@@ -373,8 +375,8 @@ __global__ void __launch_bounds__(WARPS * 32, BLP_LIGHT_MIN_CTAS) k_score_light(
                         own[h] = seg_search(incl, ii);
                         const int off = ii - __shfl_sync(kFull, excl, own[h]);
                         const long long at = __shfl_sync(kFull, pat, own[h]) + off;
-                        v[h] = ok[h] ? ldg_stream(adj4 + at) : sent4;
-                        wt[h] = ok[h] ? ldg_stream_u(adjw4 + at) : make_uint4(0u, 0u, 0u, 0u);
+                        v[h] = ok[h] ? ldg_stream(adj4 + at, pol) : sent4;
+                        wt[h] = ok[h] ? ldg_stream_u(adjw4 + at, pol) : make_uint4(0u, 0u, 0u, 0u);
                     }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLP_LIGHT_MIN_CTAS) k_score_light(
                                 run_cnt = 0;
                                 run_acc = 0ull;
                             }
-                            light_test4<SLOTS>(ls.table, v[h], wt[h], x, hbm, run_cnt, run_acc);
+                            light_test4<SLOTS>(ls.table, v[h], wt[h], x, hbm, run_cnt, run_acc, pol);
                         }
                     }
                 }
@@ -415,17 +417,17 @@ __global__ void __launch_bounds__(WARPS * 32, BLP_LIGHT_MIN_CTAS) k_score_light(
                 const double av = (double)my_aa * (1.0 / (double)(1ull << BLP_AA_FRAC_BITS));
                 if (REC) {
                     unsigned long long* rr = a.rec + 3 * (tb + lane);
-                    rr[0] = (unsigned long long)(unsigned)cnn | ((unsigned long long)(unsigned)u << 32);
-                    rr[1] = (unsigned long long)__double_as_longlong(jv);
-                    rr[2] = (unsigned long long)__double_as_longlong(av);
+                    st_stream(rr, (unsigned long long)(unsigned)cnn | ((unsigned long long)(unsigned)u << 32));
+                    st_stream(rr + 1, (unsigned long long)__double_as_longlong(jv));
+                    st_stream(rr + 2, (unsigned long long)__double_as_longlong(av));
                 } else {
-                    if (a.cn) a.cn[idx] = cnn;
-                    if (a.uni) a.uni[idx] = u;
-                    if (a.jac) a.jac[idx] = jv;
-                    if (a.aa) a.aa[idx] = av;
+                    if (a.cn) st_stream(a.cn + idx, cnn);
+                    if (a.uni) st_stream(a.uni + idx, u);
+                    if (a.jac) st_stream(a.jac + idx, jv);
+                    if (a.aa) st_stream(a.aa + idx, av);
                 }
-                if (a.pa) a.pa[idx] = (long long)xdeg * (long long)pdeg;
-                if (a.hop2) a.hop2[idx] = hop2;
+                if (a.pa) st_stream(a.pa + idx, (long long)xdeg * (long long)pdeg);
+                if (a.hop2) st_stream(a.hop2 + idx, hop2);
             }
             __syncwarp();
         }
