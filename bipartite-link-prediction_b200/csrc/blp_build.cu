@@ -404,6 +404,90 @@ int radix_sort_u64(unsigned long long* keys, unsigned long long* tmp, long long 
     *sorted = keys;
     return rc;
 }
+// ------------------------------------------------------------------------------------ id ranges
+// One warp per row of a ranged side's middle adjacency: count the ids of every id range, write the
+// exclusive prefix to seg_off[row][0..R] and -- unless the row is known to ascend already -- move
+// the ids so that range 0's come first, then range 1's, ... (order inside a range is free).  The
+// padding at the row's tail (sentinel ids) is not touched and belongs to no segment.
+namespace {
+__global__ void __launch_bounds__(256) k_range_segments(const unsigned long long* __restrict__ row_desc,
+                                                        int n_rows, int* __restrict__ adj,
+                                                        int* __restrict__ tmp, int range_bits, int n_ranges,
+                                                        int reorder, int* __restrict__ seg_off,
+                                                        int* __restrict__ next_row) {
+    __shared__ int s_cnt[8][kMaxRanges + 1], s_cur[8][kMaxRanges + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(next_row, 1);
+        r = __shfl_sync(kFullMask, r, 0);
+        if (r >= n_rows) break;
+        const unsigned long long d = row_desc[r];
+        const int len = (int)(d & 0xffffffull);
+        const long long first = (long long)((d >> 24) & ((1ull << BLP_ROW_FIRST4_BITS) - 1)) * 4;
+        int* row = adj + first;
+        for (int k = lane; k <= n_ranges; k += 32) s_cnt[warp][k] = 0;
+        __syncwarp();
+        for (int i = lane; i < len; i += 32) atomicAdd(&s_cnt[warp][row[i] / range_bits + 1], 1);
+        __syncwarp();
+        if (lane == 0) {
+            int run = 0;
+            for (int k = 0; k <= n_ranges; ++k) {
+                run += s_cnt[warp][k];
+                s_cnt[warp][k] = run;      // exclusive prefix: s_cnt[k] = ids of ranges < k
+                s_cur[warp][k] = run;
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k <= n_ranges; k += 32) seg_off[(size_t)r * (n_ranges + 1) + k] = s_cnt[warp][k];
+        if (reorder && len > 1) {
+            int* t = tmp + first;
+            for (int i = lane; i < len; i += 32) {
+                const int id = row[i];
+                t[atomicAdd(&s_cur[warp][id / range_bits], 1)] = id;
+            }
+            __syncwarp();
+            for (int i = lane; i < len; i += 32) row[i] = t[i];
+        }
+        __syncwarp();
+    }
+}
+}  // namespace
+
+int build_range_segments(blp_graph* g, bool reorder, int* tmp, cudaStream_t st) {
+    for (int side = 0; side < 2; ++side) {
+        const int R = g->n_ranges[side];
+        if (R <= 1) continue;
+        if (R > kMaxRanges) {
+            set_error("graph needs more id ranges than this build supports");
+            return BLP_ERR_UNSUPPORTED;
+        }
+        const bool us = side == BLP_SIDE_USER;
+        const int n_mid = us ? g->n_biz : g->n_users;
+        int* adj = us ? g->b_adj : g->u_adj;
+        const unsigned long long* rows = (const unsigned long long*)(us ? g->b_row : g->u_row);
+        const size_t cells = (size_t)n_mid * (size_t)(R + 1);
+        BLP_CUDA_TRY(cudaMalloc((void**)&g->seg_off[side], sizeof(int) * cells));
+        g->device_bytes += (int64_t)(sizeof(int) * cells);
+        int* counter = nullptr;
+        BLP_CUDA_TRY(cudaMalloc((void**)&counter, sizeof(int)));
+        BLP_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), st));
+        int* scratch = tmp;
+        if (reorder && !scratch) {
+            const long long len = us ? g->b_adj_len : g->u_adj_len;
+            BLP_CUDA_TRY(cudaMalloc((void**)&scratch, sizeof(int) * (size_t)std::max<long long>(len, 1)));
+        }
+        k_range_segments<<<g->sm_count * 4, 256, 0, st>>>(rows, n_mid, adj, scratch, g->range_words[side] * 32,
+                                                          R, reorder ? 1 : 0, g->seg_off[side], counter);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(counter);
+        if (scratch != tmp) cudaFree(scratch);
+        if (e != cudaSuccess) return cuda_fail(e, "k_range_segments", __FILE__, __LINE__);
+    }
+    return BLP_OK;
+}
+
 }  // namespace blp
 
 extern "C" int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n_edges,
@@ -583,11 +667,16 @@ extern "C" int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n
                                                              (unsigned long long*)g->u_row, g->u_deg);
     k_row_descriptors<<<(n_biz + 255) / 256, 256, 0, st>>>(b_off, b_deg, n_biz,
                                                            (unsigned long long*)g->b_row, g->b_deg);
+    // a side that needs id-range passes gets its middle rows partitioned by range instead of
+    // bank-striped: business rows serve the user side, user rows the business side
     if (g->tune.bank_stripe) {   // (BLP_NO_BANK_STRIPE, read at handle creation)
-        k_bank_stripe<<<g->sm_count * 4, 256, 0, st>>>(u_off, u_deg, n_users, g->u_adj, tmp, next_row);
-        k_bank_stripe<<<g->sm_count * 4, 256, 0, st>>>(b_off, b_deg, n_biz, g->b_adj, tmp, next_row + 1);
+        if (g->n_ranges[1] == 1)
+            k_bank_stripe<<<g->sm_count * 4, 256, 0, st>>>(u_off, u_deg, n_users, g->u_adj, tmp, next_row);
+        if (g->n_ranges[0] == 1)
+            k_bank_stripe<<<g->sm_count * 4, 256, 0, st>>>(b_off, b_deg, n_biz, g->b_adj, tmp, next_row + 1);
     }
     BLP_TRY_B(cudaGetLastError());
+    BLP_RC_B(build_range_segments(g, /*reorder=*/true, tmp, st));
 
     // ---- per-entry weights from a host-evaluated 1/ln(d) table
     {

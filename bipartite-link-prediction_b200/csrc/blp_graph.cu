@@ -162,6 +162,9 @@ int init_device_state(blp_graph* g, int device) {
     for (int sd = 0; sd < 2; ++sd)
         BLP_CUDA_TRY(cudaEventCreateWithFlags(&g->ev_fork[sd], cudaEventDisableTiming));
     BLP_CUDA_TRY(cudaStreamCreateWithFlags(&g->side_stream, cudaStreamNonBlocking));
+    // id-range plan of both sides (n_users / n_biz are set by the builders before this call)
+    range_plan(g->n_users, g->max_smem_optin, g->tune.ranges, &g->n_ranges[0], &g->range_words[0]);
+    range_plan(g->n_biz, g->max_smem_optin, g->tune.ranges, &g->n_ranges[1], &g->range_words[1]);
     for (int sd = 0; sd < 2; ++sd) {
         BLP_CUDA_TRY(cudaMalloc((void**)&g->d_counts[sd], sizeof(int) * 2));
         BLP_CUDA_TRY(cudaMemset(g->d_counts[sd], 0, sizeof(int) * 2));
@@ -281,13 +284,21 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
         std::vector<uint64_t>().swap(keys);
         blp_tuning tune;
         blp::read_tuning(&tune);
+        // a side that needs id-range passes keeps its middle rows ascending (= partitioned by
+        // range): business rows serve the user side, user rows the business side
+        int optin = 0, nr_user = 1, nr_biz = 1, rw = 0;
+        BLP_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        blp::range_plan(n_users, optin, tune.ranges, &nr_user, &rw);
+        blp::range_plan(n_biz, optin, tune.ranges, &nr_biz, &rw);
         if (tune.bank_stripe) {   // (BLP_NO_BANK_STRIPE: tuning switch)
             std::vector<int32_t> tmp;
             std::vector<int32_t> bucket[32];
-            for (int32_t u = 0; u < n_users; ++u)
-                if (u_deg[u] > 16) blp::bank_stripe_row(&u_adj[u_off[u]], u_deg[u], tmp, bucket);
-            for (int32_t b = 0; b < n_biz; ++b)
-                if (b_deg[b] > 16) blp::bank_stripe_row(&b_adj[b_off[b]], b_deg[b], tmp, bucket);
+            if (nr_biz == 1)
+                for (int32_t u = 0; u < n_users; ++u)
+                    if (u_deg[u] > 16) blp::bank_stripe_row(&u_adj[u_off[u]], u_deg[u], tmp, bucket);
+            if (nr_user == 1)
+                for (int32_t b = 0; b < n_biz; ++b)
+                    if (b_deg[b] > 16) blp::bank_stripe_row(&b_adj[b_off[b]], b_deg[b], tmp, bucket);
         }
 
         g = new blp_graph();
@@ -333,6 +344,7 @@ extern "C" int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
         if (rc == BLP_OK) rc = blp::upload(&g->b_deg, b_deg, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->u_adjw, u_adjw, &g->device_bytes);
         if (rc == BLP_OK) rc = blp::upload(&g->b_adjw, b_adjw, &g->device_bytes);
+        if (rc == BLP_OK) rc = blp::build_range_segments(g, /*reorder=*/false, nullptr, nullptr);
         if (rc == BLP_OK) rc = blp::build_hub_bitmaps(g, u_deg.data(), b_deg.data());
         if (rc != BLP_OK) {
             std::string keep = blp_last_error();
@@ -363,6 +375,7 @@ extern "C" int blp_graph_destroy(blp_graph* g) {
     cudaFree(g->u_adjw);
     cudaFree(g->b_adjw);
     for (int sd = 0; sd < 2; ++sd) {
+        cudaFree(g->seg_off[sd]);
         cudaFree(g->xrow[sd]);
         cudaFree(g->hub_bm[sd]);
         cudaFree(g->node_wt[sd]);

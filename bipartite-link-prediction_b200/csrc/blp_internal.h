@@ -85,6 +85,14 @@ struct blp_graph {
     int* hubtab_cn[2] = {nullptr, nullptr};
     unsigned long long* hubtab_aa[2] = {nullptr, nullptr};
     unsigned* node_wt[2] = {nullptr, nullptr};    // Q1.31 1/ln(deg) per grouping-side node of side s
+    // Id ranges.  When the bitmap over side s's universe does not fit one CTA's shared memory (or
+    // BLP_RANGES asks for it) k_score_side processes every group of side s once per id range.  The
+    // rows of that side's MIDDLE adjacency are then kept partitioned by range (not bank-striped):
+    // seg_off[s][m * (n_ranges+1) + r] is the entry offset inside row m where range r's ids begin,
+    // so a pass streams only the segment it can use instead of filtering the whole list again.
+    int n_ranges[2] = {1, 1};
+    int range_words[2] = {0, 0};                      // bitmap words of one range (multiple of 4)
+    int* seg_off[2] = {nullptr, nullptr};
     int hub_min_deg[2] = {0x7fffffff, 0x7fffffff};    // expansion ORs the bitmap from here on
     int probe_min_deg[2] = {0x7fffffff, 0x7fffffff};  // a bitmap exists from here on
     int n_hubs[2] = {0, 0};                           // bitmaps kept (both kinds)
@@ -103,6 +111,12 @@ namespace blp {
 // words of the shared-memory bitmap over n_side nodes (+1 sentinel bit), multiple of 4
 inline int bitmap_words(int n_side) { return (int)((((long long)n_side + 1 + 31) / 32 + 3) & ~3LL); }
 int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host);
+// how many id-range passes side `n_side` needs on a device with `smem_optin` bytes per CTA
+void range_plan(int n_side, int smem_optin, int forced, int* n_ranges, int* range_words);
+constexpr int kMaxRanges = 255;
+// partition the middle rows of every ranged side by id range (reorder = false: rows already ascend)
+// and fill seg_off; `tmp` = scratch of max(u_adj_len, b_adj_len) ints when reordering
+int build_range_segments(blp_graph* g, bool reorder, int* tmp, cudaStream_t st);
 int init_device_state(blp_graph* g, int device);
 void host_state_destroy(blp_graph* g);
 void weight_lut(int32_t max_deg, std::vector<unsigned>& lut);

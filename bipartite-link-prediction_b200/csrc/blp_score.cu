@@ -529,7 +529,8 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             int nch = 0;
             int list_len = 0;
             if (tid < count) {
-                unsigned long long row = (tb == 0 && pass == 0) ? cur.rowx : a.m_xrow[xadj[tb + tid]];
+                const int m_id = tb == 0 ? cur.m : xadj[tb + tid];   // (the first tile's neighbour is in a register)
+                unsigned long long row = (tb == 0 && pass == 0) ? cur.rowx : a.m_xrow[m_id];
                 list_len = min(row_deg(row), kProbeCap + 1);
                 if (row >> 63) {
                     const int h = atomicAdd(&ts.nhub, 1);
@@ -537,6 +538,8 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                     ts.cn[h] = row_deg(row);   // ts.cn is idle during the expansion
                     row = 0ull;                // degree 0: skipped by both list walkers
                     list_len = kProbeCap + 1;
+                } else if (RANGED) {
+                    row = segment_row(a, row, m_id, pass);   // only this range's part of the list
                 }
                 ts.row[tid] = row;
                 nch = long_chunks(row);
@@ -662,7 +665,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             const int count = (int)min((long long)kTile, p1 - tb);
             int nch = 0;
             if (tid < count) {
-                const bool first = tb == p0 && pass == 0;
+                const bool first = !RANGED && tb == p0 && pass == 0;
                 unsigned long long row;
                 if (first) {
                     row = ts.aa[tid];
@@ -670,6 +673,10 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
                     const int2 iy = pair_at(a, tb + tid);
                     row = a.m_row[iy.y];
                     ts.idx[tid] = iy.x;
+                    if (RANGED) {
+                        ts.hub[tid] = row_deg(row);              // deg(y) for the epilogue (hub[] is idle here)
+                        row = segment_row(a, row, iy.y, pass);   // only this range's part of N(y)
+                    }
                 }
                 ts.row[tid] = row;
                 ts.cn[tid] = 0;
@@ -704,7 +711,7 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             if (tid < count && final_pass) {
                 int idx = ts.idx[tid];
                 int c = ts.cn[tid];
-                int pdeg = row_deg(ts.row[tid]);
+                int pdeg = RANGED ? ts.hub[tid] : row_deg(ts.row[tid]);
                 int u = hop2 + pdeg - c;   // |a| + |b| - |a & b|  (similarity.py:110)
                 const double jv = __ddiv_rn((double)c, (double)u);
                 const double av = (double)ts.aa[tid] * (1.0 / (double)(1ull << BLP_AA_FRAC_BITS));
@@ -773,6 +780,23 @@ static int occupancy(size_t smem, int* ctas_per_sm) {
     BLP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         ctas_per_sm, k_score_side<NT, RANGED, REC>, NT, smem));
     return BLP_OK;
+}
+
+// The bitmap must hold bits 0..n_side (the last one is the padding sentinel).  When that does not
+// fit in one CTA's shared memory the id universe is cut into equal ranges and every group is
+// processed once per range (BLP_RANGES forces a count, for tuning / tests).
+void range_plan(int n_side, int smem_optin, int forced, int* n_ranges_out, int* range_words_out) {
+    const int full_words = bitmap_words(n_side);
+    const long long cap_words = (((long long)smem_optin - (long long)sizeof(TileSmem) - 256) / 4) & ~3LL;
+    int n_ranges = (int)((full_words + cap_words - 1) / cap_words);
+    n_ranges = std::max(n_ranges, forced);
+    int range_words = full_words;
+    if (n_ranges > 1) {
+        range_words = (int)((((long long)full_words + n_ranges - 1) / n_ranges + 3) & ~3LL);
+        n_ranges = (full_words + range_words - 1) / range_words;
+    }
+    *n_ranges_out = n_ranges;
+    *range_words_out = range_words;
 }
 
 // One CTA per hub: write its neighbour list into its (already zeroed) bitmap.
@@ -984,21 +1008,19 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     a.pa = (long long*)pa;
     a.hop2 = hop2_size;
 
-    // The bitmap must hold bits 0..n_side (the last one is the padding sentinel).  When that does
-    // not fit in one CTA's shared memory the id universe is cut into equal ranges and every group
-    // is processed once per range (BLP_RANGES forces a count, for tuning).
+    // id-range passes: planned when the handle was created (range_plan), because the middle rows
+    // of a ranged side are laid out partitioned by range
     const int full_words = bitmap_words(a.n_side);
     a.hub_words = full_words;
-    const long long cap_words =
-        (((long long)g->max_smem_optin - (long long)sizeof(TileSmem) - 256) / 4) & ~3LL;
-    int n_ranges = (int)((full_words + cap_words - 1) / cap_words);
-    n_ranges = std::max(n_ranges, g->tune.ranges);   // (BLP_RANGES, read at handle creation)
-    int range_words = full_words;
-    if (n_ranges > 1) {
-        range_words = (int)((((long long)full_words + n_ranges - 1) / n_ranges + 3) & ~3LL);
-        n_ranges = (full_words + range_words - 1) / range_words;
-    }
+    const int n_ranges = g->n_ranges[side];
+    const int range_words = g->range_words[side];
     const bool ranged = n_ranges > 1;
+    if (ranged && !g->seg_off[side]) {
+        set_error("blp_score_pairs: internal error: ranged side without range segments");
+        return BLP_ERR_UNSUPPORTED;
+    }
+    a.seg_off = g->seg_off[side];
+    a.seg_stride = n_ranges + 1;
     a.bm_words = range_words;
     a.range_bits = range_words * 32;
     a.n_ranges = n_ranges;

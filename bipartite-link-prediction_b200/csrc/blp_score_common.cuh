@@ -47,6 +47,10 @@ struct SideArgs {
     // [r*range_bits, (r+1)*range_bits); partial cn / aa wait in scratch (grouped order)
     int range_bits;
     int n_ranges;
+    // ranged sides: middle rows are partitioned by range; seg_off[m * seg_stride + r] = offset of
+    // range r's first entry inside row m (seg_stride = n_ranges + 1)
+    const int* __restrict__ seg_off;
+    int seg_stride;
     int* acc_cn;
     unsigned long long* acc_aa;
     // grouping
@@ -213,6 +217,19 @@ enum { MODE_SORT = 0, MODE_RUNS = 1 };
 // (caller-order index, partner) of the pair at grouped position k
 __device__ __forceinline__ int2 pair_at(const SideArgs& a, long long k) {
     return a.pg ? ld_once(a.pg + k) : make_int2((int)k, ld_once(a.caller_y + k));
+}
+
+// Descriptor of the part of row `row` (of middle node m) that holds the ids of range `pass`: the
+// 16-byte aligned window around entries [s, e) of the row.  Entries of the window outside [s, e)
+// belong to neighbouring ranges or are padding and fail the walker's range test.  The degree field
+// is set so that (deg + 3) / 4 is the window's length in 128-bit words (0 = nothing to walk).
+__device__ __forceinline__ unsigned long long segment_row(const SideArgs& a, unsigned long long row, int m,
+                                                          int pass) {
+    const int* so = a.seg_off + (size_t)m * a.seg_stride + pass;
+    const int s = so[0], e = so[1];
+    const long long f4 = row_first4(row) + (s >> 2);
+    const int n4 = e > s ? ((e + 3) >> 2) - (s >> 2) : 0;
+    return ((unsigned long long)f4 << 24) | (unsigned)(n4 << 2);
 }
 
 constexpr int kShortV4 = 4;   // lists of <= 16 ids take the sub-warp path (4 lanes per list)

@@ -185,13 +185,16 @@ def test_id_range_passes_do_not_change_results(mods, monkeypatch):
     G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
     one = G.score_pairs_host(pu, pv, want_hop2=True)
     assert G.score_stats(lib.SIDE_USER)['range_passes'] == 1
-    for r in ('2', '5'):
+    for r, build in (('2', 'device'), ('5', 'device'), ('3', 'host'), ('7', 'host')):
+        # a ranged side keeps its middle rows partitioned by range (both builders), and a pass
+        # walks only its segment of every list
         monkeypatch.setenv('BLP_RANGES', r)
-        G2 = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+        G2 = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, build=build)
         many = G2.score_pairs_host(pu, pv, want_hop2=True)
         assert G2.score_stats(lib.SIDE_USER)['range_passes'] == int(r)
+        assert G2.score_stats(lib.SIDE_BUSINESS)['range_passes'] == int(r)
         for k in one:
-            assert np.array_equal(one[k], many[k]), (r, k)
+            assert np.array_equal(one[k], many[k]), (r, build, k)
     monkeypatch.delenv('BLP_RANGES')
     again = G.score_pairs_host(pu, pv, want_hop2=True)      # the first handle never saw the variable
     assert G.score_stats(lib.SIDE_USER)['range_passes'] == 1
@@ -231,12 +234,14 @@ def test_universe_larger_than_shared_memory(mods):
     n_users, n_biz = 2_500_000, 3000
     eu, eb = synth.make_graph(n_users, n_biz, 400_000, seed=5, shift_u=50.0, shift_b=5.0)
     pu, pv = synth.make_pairs(n_users, n_biz, eu, eb, 20_000, k=8, seed=6)
-    G = graph.BipartiteGraph(n_users, n_biz, eu, eb)
-    got = G.score_pairs_host(pu, pv)
-    assert G.score_stats(lib.SIDE_USER)['range_passes'] >= 2
-    assert G.score_stats(lib.SIDE_BUSINESS)['range_passes'] == 1
     want = c_oracle.score_pair_arrays(n_users, n_biz, eu, eb, pu, pv)
-    check_against(got, want, pu.size)
+    for build in ('device', 'host'):
+        G = graph.BipartiteGraph(n_users, n_biz, eu, eb, build=build)
+        got = G.score_pairs_host(pu, pv)
+        assert G.score_stats(lib.SIDE_USER)['range_passes'] >= 2
+        assert G.score_stats(lib.SIDE_BUSINESS)['range_passes'] == 1
+        check_against(got, want, pu.size)
+        G.close()
 
 
 @pytest.mark.timeout(600)
