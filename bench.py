@@ -288,7 +288,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -299,8 +299,20 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi needs a moment before its first line: do not start timing without one."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.05)
+
     def window(self, t0, t1):
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        # samples taken inside the timed region; a region shorter than the sampling interval
+        # takes the samples that bracket it
+        if self.proc is not None:
+            time.sleep(0.12)
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        if not rows:
+            rows = [r for t, r in self.rows if t0 - 0.15 <= t <= t1 + 0.15] or [r for _, r in self.rows[-3:]]
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in rows:
@@ -512,12 +524,13 @@ def main():
             st_b.append(G.score_stats(_lib.SIDE_BUSINESS))
         return tot, st_u, st_b
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(a.warmup):
         flush.zero_()
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.3 if sampler else 0.0)
+    if sampler:
+        sampler.wait_first()
     barrier()
     t_wall0 = time.perf_counter()
     total_ms, st_u, st_b = timed(a.steps)
@@ -617,6 +630,7 @@ def main():
     hu[:] = pu
     hb[:] = pv
     e2e_steps = max(3, min(a.steps, 10))
+    link = sess.measure_link(n) if rank == 0 else None     # (scribbles over the result buffers: first)
     for _ in range(2):
         sess.score_pinned(n)
     barrier()
@@ -625,7 +639,6 @@ def main():
         host = sess.score_pinned(n)
     torch.cuda.synchronize()
     e2e_s = reduce_max(time.perf_counter() - t0) / e2e_steps
-    link = sess.measure_link(n) if rank == 0 else None
     e2e = {'value': n_total / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
            'h2d_bytes_per_step': sess.h2d_bytes_per_pair * n,
            'd2h_bytes_per_step': sess.d2h_bytes_per_pair * n, 'steps': e2e_steps,

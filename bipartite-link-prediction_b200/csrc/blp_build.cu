@@ -119,8 +119,8 @@ struct Scanner {
         const long long nb = (n + kSortTile - 1) / kSortTile;
         if (nb <= cap) return BLP_OK;
         if (sums) cudaFreeAsync(sums, st);
-        BLP_CUDA_TRY(cudaMallocAsync((void**)&sums, sizeof(unsigned long long) * (size_t)(nb + 1), st));
-        if (!total) BLP_CUDA_TRY(cudaMallocAsync((void**)&total, sizeof(unsigned long long), st));
+        BLP_CUDA_TRY(scratch_alloc((void**)&sums, sizeof(unsigned long long) * (size_t)(nb + 1), st));
+        if (!total) BLP_CUDA_TRY(scratch_alloc((void**)&total, sizeof(unsigned long long), st));
         cap = nb;
         return BLP_OK;
     }
@@ -381,11 +381,11 @@ int radix_sort_u64(unsigned long long* keys, unsigned long long* tmp, long long 
     const int n_tiles = (int)((n + kSortTile - 1) / kSortTile);
     unsigned* hist = nullptr;
     unsigned long long* hbase = nullptr;
-    BLP_CUDA_TRY(cudaMallocAsync((void**)&hist, sizeof(unsigned) * 256 * (size_t)n_tiles, st));
-    cudaError_t e = cudaMallocAsync((void**)&hbase, sizeof(unsigned long long) * 256 * (size_t)n_tiles, st);
+    BLP_CUDA_TRY(scratch_alloc((void**)&hist, sizeof(unsigned) * 256 * (size_t)n_tiles, st));
+    cudaError_t e = scratch_alloc((void**)&hbase, sizeof(unsigned long long) * 256 * (size_t)n_tiles, st);
     if (e != cudaSuccess) {
         cudaFreeAsync(hist, st);
-        return cuda_fail(e, "cudaMallocAsync(hbase)", __FILE__, __LINE__);
+        return cuda_fail(e, "scratch_alloc(hbase)", __FILE__, __LINE__);
     }
     Scanner scan;
     scan.st = st;
@@ -528,7 +528,7 @@ extern "C" int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n
     g->n_edges_in = n_edges;
     std::vector<void*> scratch;
     auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
-        cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, st);
+        cudaError_t e = scratch_alloc(p, bytes ? bytes : 16, st);
         if (e == cudaSuccess) scratch.push_back(*p);
         return e;
     };

@@ -150,10 +150,10 @@ extern "C" int blp_eval_roc_auc(const int32_t* labels, const double* scores, int
         cudaError_t e__ = (expr);                                                    \
         if (e__ != cudaSuccess) return done(cuda_fail(e__, #expr, __FILE__, __LINE__)); \
     } while (0)
-    BLP_TRY_E(cudaMallocAsync((void**)&pos, sizeof(unsigned long long) * (size_t)n, st));
-    BLP_TRY_E(cudaMallocAsync((void**)&neg, sizeof(unsigned long long) * (size_t)n, st));
-    BLP_TRY_E(cudaMallocAsync((void**)&tmp, sizeof(unsigned long long) * (size_t)n, st));
-    BLP_TRY_E(cudaMallocAsync((void**)&counters, sizeof(unsigned long long) * 4, st));
+    BLP_TRY_E(scratch_alloc((void**)&pos, sizeof(unsigned long long) * (size_t)n, st));
+    BLP_TRY_E(scratch_alloc((void**)&neg, sizeof(unsigned long long) * (size_t)n, st));
+    BLP_TRY_E(scratch_alloc((void**)&tmp, sizeof(unsigned long long) * (size_t)n, st));
+    BLP_TRY_E(scratch_alloc((void**)&counters, sizeof(unsigned long long) * 4, st));
     BLP_TRY_E(cudaMemsetAsync(counters, 0, sizeof(unsigned long long) * 4, st));
     const long long sms = current_sm_count();
     const int blocks = (int)std::min<long long>((n + 255) / 256, sms * 16);

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -132,7 +133,66 @@ static void entry_weights(const std::vector<int32_t>& adj, int32_t sentinel,
         adjw[k] = adj[k] == sentinel ? 0u : lut[deg_of_entry_side[adj[k]]];
 }
 
-// Device properties, a warm stream-ordered memory pool and the timing events of a new handle.
+// Stream-ordered scratch (graph construction on the device, the per-call scratch of the scoring
+// kernels) comes from ONE pool per device that the library owns and shares between its handles:
+// its release threshold is the maximum, so repeated calls and repeated graph builds reuse the same
+// memory instead of going back to the driver at every synchronisation.  The device's default pool
+// keeps its settings.  When the last handle on a device is destroyed the pool is trimmed to zero,
+// so nothing stays cached once the application is done with the library.
+namespace {
+constexpr int kPoolDevices = 64;
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pool[kPoolDevices] = {};
+int g_pool_refs[kPoolDevices] = {};
+}  // namespace
+
+cudaMemPool_t acquire_scratch_pool(int device) {
+    if (device < 0 || device >= kPoolDevices) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pool[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&g_pool[device], &props) != cudaSuccess) {
+            (void)cudaGetLastError();
+            g_pool[device] = nullptr;
+            return nullptr;
+        }
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(g_pool[device], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    ++g_pool_refs[device];
+    return g_pool[device];
+}
+
+// stream-ordered allocation for code that has no handle at hand (sort, scan, evaluation): the
+// library pool of the current device while some handle keeps it alive, else the default pool
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+    int device = -1;
+    if (cudaGetDevice(&device) == cudaSuccess && device >= 0 && device < kPoolDevices) {
+        cudaMemPool_t pool = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(g_pool_mutex);
+            if (g_pool_refs[device] > 0) pool = g_pool[device];
+        }
+        if (pool) return cudaMallocFromPoolAsync(p, bytes, pool, st);
+    }
+    return cudaMallocAsync(p, bytes, st);
+}
+
+void release_scratch_pool(int device) {
+    if (device < 0 || device >= kPoolDevices) return;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool[device] && --g_pool_refs[device] <= 0) {
+        g_pool_refs[device] = 0;
+        cudaMemPoolTrimTo(g_pool[device], 0);   // last handle gone: give the cached scratch back
+        (void)cudaGetLastError();
+    }
+}
+
+// Device properties, the scratch pool and the timing events of a new handle.
 int init_device_state(blp_graph* g, int device) {
     cudaDeviceProp prop;
     BLP_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -140,23 +200,7 @@ int init_device_state(blp_graph* g, int device) {
     g->sm_count = prop.multiProcessorCount;
     g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     read_tuning(&g->tune);
-    // a pool of the handle's own for the stream-ordered scratch of its scoring calls, kept cached
-    // instead of being returned to the driver at every synchronisation (release threshold = max);
-    // the device's default pool keeps its settings
-    {
-        cudaMemPoolProps props = {};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = device;
-        if (cudaMemPoolCreate(&g->pool, &props) == cudaSuccess) {
-            uint64_t keep = UINT64_MAX;
-            cudaMemPoolSetAttribute(g->pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        } else {
-            g->pool = nullptr;   // fall back to the default pool, untouched
-        }
-        (void)cudaGetLastError();
-    }
+    g->pool = acquire_scratch_pool(device);   // nullptr: fall back to the default pool, untouched
     for (int sd = 0; sd < 2; ++sd)
         for (int k = 0; k < 4; ++k) BLP_CUDA_TRY(cudaEventCreate(&g->ev[sd][k]));
     for (int sd = 0; sd < 2; ++sd)
@@ -390,7 +434,7 @@ extern "C" int blp_graph_destroy(blp_graph* g) {
         if (g->ev_fork[sd]) cudaEventDestroy(g->ev_fork[sd]);
     if (g->side_stream) cudaStreamDestroy(g->side_stream);
     for (int sd = 0; sd < 2; ++sd) cudaFree(g->d_counts[sd]);
-    if (g->pool) cudaMemPoolDestroy(g->pool);
+    if (g->pool) blp::release_scratch_pool(g->device);
     (void)cudaGetLastError();
     delete g;
     return BLP_OK;

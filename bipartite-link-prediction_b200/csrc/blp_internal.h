@@ -40,9 +40,9 @@ struct blp_graph {
     int max_smem_optin = 0;  // bytes of dynamic shared memory one CTA may opt in to
     int reserve_sms = 0;     // SMs left out of the persistent scoring grids
     blp_tuning tune;         // developer overrides, read when the handle was created
-    // stream-ordered scratch of the scoring calls comes from a pool the handle owns (kept warm:
-    // release threshold = max), so the device's default pool and other libraries' allocators are
-    // left alone; destroyed with the handle
+    // stream-ordered scratch comes from the library's own per-device pool (shared by its handles,
+    // kept warm, trimmed when the last handle goes; see acquire_scratch_pool) -- the device's
+    // default pool and other libraries' allocators are left alone
     cudaMemPool_t pool = nullptr;
     // CTAs per SM of the scoring-kernel variants already configured: [nt 256/512/1024][ranged][rec]
     int occ_cache[3][2][2] = {};
@@ -125,6 +125,9 @@ int radix_sort_u64(unsigned long long* keys, unsigned long long* tmp, long long 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void read_tuning(blp_tuning* t);
+cudaMemPool_t acquire_scratch_pool(int device);
+void release_scratch_pool(int device);
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st);
 // stream-ordered scratch from the handle's own pool
 inline cudaError_t pool_alloc(blp_graph* g, void** p, size_t bytes, cudaStream_t st) {
     return g->pool ? cudaMallocFromPoolAsync(p, bytes, g->pool, st) : cudaMallocAsync(p, bytes, st);

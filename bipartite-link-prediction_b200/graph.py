@@ -405,7 +405,8 @@ class HostSession(object):
 
     def measure_link(self, n, reps=3):
         """The host link under this session's own buffers: pinned D2H of the result columns and
-        H2D of the pair ids, timed alone.  The copy-back time is the floor under one step."""
+        H2D of the pair ids, timed alone.  The copy-back time is the floor under one step.
+        OVERWRITES the session's pinned result buffers (call it before scoring, not after)."""
         n = min(int(n), self.n_max)
         dev = self.g.device
         with torch.cuda.device(dev):

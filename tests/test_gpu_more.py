@@ -192,7 +192,7 @@ def test_id_range_passes_do_not_change_results(mods, monkeypatch):
         G2 = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, build=build)
         many = G2.score_pairs_host(pu, pv, want_hop2=True)
         assert G2.score_stats(lib.SIDE_USER)['range_passes'] == int(r)
-        assert G2.score_stats(lib.SIDE_BUSINESS)['range_passes'] == int(r)
+        assert 2 <= G2.score_stats(lib.SIDE_BUSINESS)['range_passes'] <= int(r)   # 2000 bits: fewer, word-aligned ranges
         for k in one:
             assert np.array_equal(one[k], many[k]), (r, build, k)
     monkeypatch.delenv('BLP_RANGES')
