@@ -341,6 +341,115 @@ def _profile_json(name):
         return None
 
 
+
+# ------------------------------------------------------------------------------------ other configs
+def other_config_line(name, n_pairs, steps, rank, world, dev, cores, peak):
+    """A short line for another BASELINE.json config, beside the headline one.
+
+    N=1: `n_pairs` pairs of the config on this GPU (a stated part of the config's list when the whole
+    list would take minutes to generate).  N>1: the config's list cut N ways (strong scaling): every
+    rank generates and scores ITS contiguous share of the example users (user-aligned by
+    construction), all rows land in rank 0's peer window.  Timed like the headline (3 warm-ups,
+    L2 flushed before every step, CUDA events, max over ranks); a strided sample of the rows as
+    they sit on rank 0 is compared with the C oracle."""
+    import torch
+    import torch.distributed as dist
+    graph, roofline, _lib, dmod, synth = pkg('graph'), pkg('roofline'), pkg('_lib'), pkg('dist'), pkg('synth')
+    t_gen = time.perf_counter()
+    cfg = dict(synth.CONFIGS[name])
+    cfg['n_pairs'] = int(n_pairs)
+    eu, eb = synth.make_graph(seed=0, **cfg)
+    deg = synth.degrees(cfg['n_users'], cfg['n_biz'], eu, eb)
+    pu, pv = synth.make_pairs(edge_u=eu, edge_b=eb, seed=1, deg=deg, rank=rank, world=world, **cfg)
+    t_gen = time.perf_counter() - t_gen
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb, device=dev.index)
+    d_u, d_b = torch.from_numpy(pu).to(dev), torch.from_numpy(pv).to(dev)
+    n = int(pu.size)
+    counts = [n]
+    if world > 1:
+        t = torch.zeros(world, dtype=torch.int64, device=dev)
+        t[rank] = n
+        dist.all_reduce(t)
+        counts = [int(x) for x in t.tolist()]
+    n_total, lo = sum(counts), sum(counts[:rank])
+    window = dmod.ResultWindow(G, n_total, columns=dmod.ALL_COLUMNS, dst=0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    tot, ku, kb = 0.0, [], []
+    for it in range(3 + steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dmod.score_into_window(G, d_u, d_b, window, lo)
+        e1.record()
+        e1.synchronize()
+        if it >= 3:
+            tot += e0.elapsed_time(e1)
+            ku.append(G.score_stats(_lib.SIDE_USER))
+            kb.append(G.score_stats(_lib.SIDE_BUSINESS))
+        elif it == 2:
+            sync_all()
+    sync_all()
+    t = torch.tensor([tot], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    line = None
+    # the pairs of every rank, for the check on rank 0
+    if world > 1:
+        longest = max(counts)
+        pad_u = torch.full((longest,), -1, dtype=torch.int32, device=dev)
+        pad_b = torch.full((longest,), -1, dtype=torch.int32, device=dev)
+        pad_u[:n], pad_b[:n] = d_u, d_b
+        all_u = torch.empty(world * longest, dtype=torch.int32, device=dev)
+        all_b = torch.empty(world * longest, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_u, pad_u)
+        dist.all_gather_into_tensor(all_b, pad_b)
+    if rank == 0:
+        cols = window.tensors()
+        if world > 1:
+            keep = torch.cat([torch.arange(c, device=dev) + r * longest for r, c in enumerate(counts)])
+            pu_all, pv_all = all_u[keep].cpu().numpy(), all_b[keep].cpu().numpy()
+        else:
+            pu_all, pv_all = pu, pv
+        idx = np.arange(0, n_total, max(1, n_total // 40_000))
+        try:
+            from oracle import c_oracle
+            want = c_oracle.score_pair_arrays_parallel(cfg['n_users'], cfg['n_biz'], eu, eb, pu_all[idx],
+                                                       pv_all[idx], threads=min(cores, 8))
+            tidx = torch.from_numpy(idx).to(dev)
+            chk = compare_with_oracle({k: cols[k][tidx].cpu().numpy() for k in cols}, want)
+            chk['what'] = 'strided sample of the %d rows on rank 0 vs the C oracle' % n_total
+        except Exception as exc:
+            chk = {'error': repr(exc)}
+        u_cn = cols['u_cn'][lo:lo + n].cpu().numpy()
+        b_cn = cols['b_cn'][lo:lo + n].cpu().numpy()
+        ab = roofline.algorithmic_bytes(cfg['n_users'], cfg['n_biz'], eu, eb, pu, pv, u_cn, b_cn)
+        ku_ms = statistics.mean(s['score_ms'] for s in ku)
+        kb_ms = statistics.mean(s['score_ms'] for s in kb)
+        bytes_u = ab['user'] + ab['pa']
+        line = {'config': name, 'pairs_total': n_total, 'pairs_rank0': n, 'n_gpus': world,
+                'scaling': 'strong' if world > 1 else None,
+                'of_config': '%d of the config\'s %d pairs' % (n_total, synth.CONFIGS[name]['n_pairs']),
+                'value': n_total / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
+                'user_side_ms': ku_ms, 'business_side_ms': kb_ms,
+                'launch': {'ctas': ku[-1]['ctas'], 'threads_per_cta': ku[-1]['threads_per_cta'],
+                           'smem_bytes': ku[-1]['smem_bytes'], 'range_passes': ku[-1]['range_passes']},
+                'roofline': {'bound': 'hbm', 'kernel': 'user side (rank 0\'s share)', 'achieved': bytes_u / (ku_ms * 1e-3) / 1e9,
+                             'peak': peak, 'unit': 'GB/s', 'frac': bytes_u / (ku_ms * 1e-3) / 1e9 / peak,
+                             'algorithmic_bytes_per_launch': bytes_u,
+                             'whole_step_achieved': ab['total'] / (ms * 1e-3) / 1e9},
+                'parity_sample': chk, 'graph': G.info(), 'host_generation_s': t_gen}
+    sync_all()
+    window.close()
+    G.close()
+    return line
+
 # ------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -353,6 +462,10 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-user-groups', type=int, default=None)
     ap.add_argument('--cpu-biz-groups', type=int, default=None)
+    ap.add_argument('--no-other-configs', action='store_true',
+                    help='skip the short C3 / C4 lines that follow the headline measurement')
+    ap.add_argument('--quick', action='store_true',
+                    help='headline measurement and checks only: no comparison arms, no e2e, no other configs')
     a = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -550,7 +663,7 @@ def main():
 
     concurrent_sides, multi = None, None
     reps = max(3, min(a.steps, 10))
-    if world == 1:
+    if world == 1 and not a.quick:
         # ---- supplementary: the same call with the two sides on two streams (grids overlap)
         for _ in range(6):          # the two-stream pattern grows the stream-ordered pool first
             step(concurrent=True)
@@ -560,7 +673,26 @@ def main():
         concurrent_sides = {'ms_per_step': c_ms, 'value': n_total / (c_ms * 1e-3), 'unit': UNIT,
                             'steps': reps,
                             'what': 'score_pairs(concurrent=True): business side on a second stream'}
-    else:
+    elif world > 1 and a.quick:
+        bpp = window.bytes_per_pair()
+        multi = {'bytes_per_pair_over_nvlink': bpp, 'slice_pairs': [int(bounds[r + 1] - bounds[r]) for r in range(world)],
+                 'fused_window': {'ms_per_step': ms_per_step, 'value': value, 'unit': UNIT,
+                                  'wall_ms_per_step_with_barriers': wall_ms_per_step}}
+        if rank == 0:
+            cols = window.tensors()
+            try:
+                from oracle import c_oracle
+                idx = np.arange(0, n_total, max(1, n_total // 40_000))
+                want = c_oracle.score_pair_arrays_parallel(cfg['n_users'], cfg['n_biz'], eu, eb,
+                                                           pu_all[idx], pv_all[idx], threads=min(cores, 4))
+                tidx = torch.from_numpy(idx).to(dev)
+                chk = compare_with_oracle({k: cols[k][tidx].cpu().numpy() for k in cols}, want)
+                chk['what'] = ('strided sample over the whole %d-pair list (rows of every rank) vs the C '
+                               'oracle' % n_total)
+                multi['oracle_check'] = chk
+            except Exception as exc:
+                multi['oracle_check'] = {'error': repr(exc)}
+    elif world > 1:
         # ---- the two comparison arms: scoring into local memory, and local scoring + NCCL gather
         for _ in range(2):
             step(local=True)
@@ -625,26 +757,58 @@ def main():
         outs = None
 
     # ---- end to end through the host-buffer API (the seven reference outputs: 48 B per pair)
-    sess = G.host_session(n)
-    hu, hb = sess.pinned_inputs(n)
-    hu[:] = pu
-    hb[:] = pv
-    e2e_steps = max(3, min(a.steps, 10))
-    link = sess.measure_link(n) if rank == 0 else None     # (scribbles over the result buffers: first)
-    for _ in range(2):
-        sess.score_pinned(n)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        host = sess.score_pinned(n)
-    torch.cuda.synchronize()
-    e2e_s = reduce_max(time.perf_counter() - t0) / e2e_steps
-    e2e = {'value': n_total / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
-           'h2d_bytes_per_step': sess.h2d_bytes_per_pair * n,
-           'd2h_bytes_per_step': sess.d2h_bytes_per_pair * n, 'steps': e2e_steps,
-           'columns': list(sess.KEYS), 'link': link,
-           'api': 'BipartiteGraph.host_session().score_pinned -> one blp_score_pairs_host call '
-                  '(pinned host buffers in and out, both sides + pa; per rank at N>1)'}
+    e2e, host = None, None
+    if a.quick:
+        # no host-buffer leg: the columns the roofline / parity code needs come off the device
+        if rank == 0:
+            if world > 1:
+                cols = window.tensors()
+                host = {k: cols[k][lo:lo + n].cpu().numpy() for k in ('u_cn', 'b_cn')}
+            else:
+                host = {k: v.cpu().numpy() for k, v in outs.items()}
+    else:
+        sess = G.host_session(n)
+    hu, hb = (sess.pinned_inputs(n) if not a.quick else (None, None))
+    if not a.quick:
+        hu[:] = pu
+        hb[:] = pv
+        e2e_steps = max(3, min(a.steps, 10))
+        link = sess.measure_link(n) if rank == 0 else None     # (scribbles over the result buffers: first)
+        for _ in range(2):
+            sess.score_pinned(n)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host = sess.score_pinned(n)
+        torch.cuda.synchronize()
+        e2e_s = reduce_max(time.perf_counter() - t0) / e2e_steps
+        e2e = {'value': n_total / e2e_s, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
+               'h2d_bytes_per_step': sess.h2d_bytes_per_pair * n,
+               'd2h_bytes_per_step': sess.d2h_bytes_per_pair * n, 'steps': e2e_steps,
+               'columns': list(sess.KEYS), 'link': link,
+               'api': 'BipartiteGraph.host_session().score_pinned -> one blp_score_pairs_host call '
+                      '(pinned host buffers in and out, both sides + pa; per rank at N>1)'}
+        del sess
+
+    # ---- the other BASELINE.json configs, briefly (N=1: a part of C3 and of C4; N>1: C3 cut N ways)
+    others = None
+    if a.config == 'C2' and not a.quick and not a.no_other_configs:
+        peak_o = 6650.0
+        try:
+            peak_o = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('hbm_gbs', 6650.0))
+        except (OSError, ValueError):
+            pass
+        plan = [('C3', 20_000_000), ('C4', 10_000_000)] if world == 1 else [('C3', 100_000_000)]
+        others = []
+        for oname, opairs in plan:
+            try:
+                ol = other_config_line(oname, opairs, 3, rank, world, dev, cores, peak_o)
+            except Exception as exc:      # never lose the headline line to a side measurement
+                ol = {'config': oname, 'error': repr(exc)}
+                if world > 1:
+                    raise
+            if rank == 0:
+                others.append(ol)
 
     if rank == 0:
         peaks = {}
@@ -720,18 +884,18 @@ def main():
             fair1 = cpu_baseline['value']
             cpu_baseline['target_100x'] = {
                 'vs_fair_single_process': {'device_resident': value / fair1,
-                                           'e2e': e2e['value'] / fair1},
+                                           'e2e': e2e['value'] / fair1 if e2e else None},
                 'vs_c_port_all_cores': None}
             allc = cpu_baseline['sides'].get('c_port_all_cores_pairs_per_s')
             if allc:
                 cpu_baseline['target_100x']['vs_c_port_all_cores'] = {
-                    'device_resident': value / allc, 'e2e': e2e['value'] / allc}
+                    'device_resident': value / allc, 'e2e': e2e['value'] / allc if e2e else None}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps,
                 'warmup': a.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64', 'data': 'synthetic',
                 'config': config, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
                 'roofline': roof, 'cpu_baseline': cpu_baseline, 'parity_full_workload': parity,
-                'multi_gpu': multi, 'concurrent_sides': concurrent_sides,
+                'multi_gpu': multi, 'concurrent_sides': concurrent_sides, 'other_configs': others,
                 'graph': G.info(),
                 'graph_build': {'host_builder_s': build_host_s, 'device_builder_s': build_device_s,
                                 'edge_lines': int(eu.size),
