@@ -90,7 +90,7 @@ __device__ __forceinline__ void tile_scan(TileSmem& ts, int v, int tid, int coun
             const int c8 = __shfl_sync(kFull, ex, (lane & 3) * 8);
             ts.coarse[lane] = lane < 4 ? c8 : INT_MAX;
             if (lane == 0) ts.scan[kTile] = total;
-            if (lane < 4) ts.next_chunk[lane] = 0;
+            if (lane < 4) ts.next_chunk[lane] = NT / 32;   // chunks 0..NW-1 are dealt statically
         }
         __syncthreads();
         return;
@@ -120,7 +120,7 @@ __device__ __forceinline__ void tile_scan(TileSmem& ts, int v, int tid, int coun
         ts.scan[tid] = ex;
         if ((tid & 7) == 0) ts.coarse[tid >> 3] = ex;
         if (tid == kTile - 1) ts.scan[kTile] = base + inc;
-        if (tid < 4) ts.next_chunk[tid] = 0;
+        if (tid < 4) ts.next_chunk[tid] = NT / 32;
     }
     __syncthreads();
 }
@@ -302,15 +302,14 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
     }
     // ---- long lists
     const int total = ts.scan[kTile];
-    int c = 0;
-    if (total > 0) {
-        if (lane == 0) c = atomicAdd(&ts.next_chunk[OP], 1);
-        c = __shfl_sync(kFull, c, 0);
-    }
+    // warp w starts on chunk w without asking; further chunks come from the shared-memory
+    // dispenser (it starts at NW), which is only touched when there are more chunks than warps
+    int c = warp;
+    const bool dynamic = total > NW;
     while (c < total) {
         // claim the following chunk now: the dispenser's latency hides behind this chunk
-        int c_next = 0;
-        if (lane == 0) c_next = atomicAdd(&ts.next_chunk[OP], 1);
+        int c_next = total;
+        if (dynamic && lane == 0) c_next = atomicAdd(&ts.next_chunk[OP], 1);
         const int j = find_list(ts, c, lane);
         const unsigned long long row = ts.row[j];
         const int off4 = (c - ts.scan[j]) * kChunkV4;
@@ -357,7 +356,7 @@ __device__ __forceinline__ unsigned sweep_tile(const SideArgs& a, unsigned* bm, 
                 }
             }
         }
-        c = __shfl_sync(kFull, c_next, 0);
+        c = dynamic ? __shfl_sync(kFull, c_next, 0) : total;
     }
     return set_total;
 }
@@ -443,9 +442,11 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
 #ifdef BLP_PHASE_TIMING
     long long t_last = clock64();
 #endif
+    int ahead = 0;   // thread 0: the claim that becomes the next group's item at the next group start
     if (tid == 0) {
         mbar_init(&ts.hub_bar, 1);
         ts.item_next = atomicAdd(a.work_counter, 1);
+        ahead = atomicAdd(a.work_counter, 1);
         ts.nhub = 0;
         ts.hop2cnt = 0;
         ts.list_on = 0;
@@ -469,8 +470,11 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
     while (cur.item < n_items) {
         BLP_TICK(0);
         // claim the next item now; its descriptor is fetched in stages below
-        int claimed = 0;
-        if (tid == 0) claimed = atomicAdd(a.work_counter, 1);
+        // work-queue claims run TWO groups ahead: the index published for the next group was
+        // claimed during the previous group, so the global atomic's round trip (issued here for
+        // the group after next) is never waited for
+        const int claimed = ahead;
+        if (tid == 0) ahead = atomicAdd(a.work_counter, 1);
         GroupRegs nxt;
         const int x = cur.x;
         const long long p0 = cur.p0, p1 = cur.p1;
@@ -829,7 +833,9 @@ int build_hub_bitmaps(blp_graph* g, const int* u_deg_host, const int* b_deg_host
         const int* mdeg = us ? b_deg_host : u_deg_host;
         const int words = bitmap_words(n_side);
         const long long bm_bytes = (long long)words * 4;
-        int min_deg = (int)std::max<long long>(64, bm_bytes / 30);
+        // (round 2, with the hub copy done by TMA: C2 -- 46 KB bitmap -- 700..1000 flat and 3 % better
+        // than 1525; C3 / C4 -- 200 KB bitmap, one CTA per SM -- 6667 better than 4500 and 3000)
+        int min_deg = (int)std::max<long long>(64, bm_bytes <= 65536 ? bm_bytes / 50 : bm_bytes / 30);
         if (const char* e = getenv("BLP_HUB_MIN_DEG")) min_deg = atoi(e);   // tuning override
         // Bitmaps used only by the intersection's probe path start lower: a probe costs about as
         // much as a streamed id, and the path is taken when deg(y) >= kProbeRatio * |hop2(x)|
