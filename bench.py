@@ -380,12 +380,32 @@ def other_config_line(name, n_pairs, steps, rank, world, dev, cores, peak):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the whole pair list on rank 0 (it derives jaccard / pa for the peers' rows, and checks them)
+    all_u = all_b = None
+    if world > 1:
+        longest = max(counts)
+        pad_u = torch.full((longest,), -1, dtype=torch.int32, device=dev)
+        pad_b = torch.full((longest,), -1, dtype=torch.int32, device=dev)
+        pad_u[:n], pad_b[:n] = d_u, d_b
+        g_u = torch.empty(world * longest, dtype=torch.int32, device=dev)
+        g_b = torch.empty(world * longest, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(g_u, pad_u)
+        dist.all_gather_into_tensor(g_b, pad_b)
+        if rank == 0:
+            keep = torch.cat([torch.arange(c, device=dev) + r * longest for r, c in enumerate(counts)])
+            all_u, all_b = g_u[keep].contiguous(), g_b[keep].contiguous()
+        del g_u, g_b, pad_u, pad_b
+
     tot, ku, kb = 0.0, [], []
     for it in range(3 + steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         dmod.score_into_window(G, d_u, d_b, window, lo)
+        if world > 1:
+            dmod.rows_landed(G)
+            if rank == 0:
+                window.derive(all_u, all_b, own=(lo, lo + n))
         e1.record()
         e1.synchronize()
         if it >= 3:
@@ -400,21 +420,10 @@ def other_config_line(name, n_pairs, steps, rank, world, dev, cores, peak):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / steps
     line = None
-    # the pairs of every rank, for the check on rank 0
-    if world > 1:
-        longest = max(counts)
-        pad_u = torch.full((longest,), -1, dtype=torch.int32, device=dev)
-        pad_b = torch.full((longest,), -1, dtype=torch.int32, device=dev)
-        pad_u[:n], pad_b[:n] = d_u, d_b
-        all_u = torch.empty(world * longest, dtype=torch.int32, device=dev)
-        all_b = torch.empty(world * longest, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(all_u, pad_u)
-        dist.all_gather_into_tensor(all_b, pad_b)
     if rank == 0:
         cols = window.tensors()
         if world > 1:
-            keep = torch.cat([torch.arange(c, device=dev) + r * longest for r, c in enumerate(counts)])
-            pu_all, pv_all = all_u[keep].cpu().numpy(), all_b[keep].cpu().numpy()
+            pu_all, pv_all = all_u.cpu().numpy(), all_b.cpu().numpy()
         else:
             pu_all, pv_all = pu, pv
         idx = np.arange(0, n_total, max(1, n_total // 40_000))
@@ -618,7 +627,12 @@ def main():
         # stream, so that the per-kernel event times below are those of the kernels alone
         nonlocal outs
         if window is not None and not local:
+            # peers store cn / union / adamic of both sides (32 B per pair) into rank 0's window;
+            # rank 0 derives jaccard and pa for their rows once every rank's kernels are done
             dmod.score_into_window(G, d_u, d_b, window, lo)
+            dmod.rows_landed(G)
+            if rank == 0:
+                window.derive(all_u, all_b, own=(lo, hi))
         else:
             outs = G.score_pairs(d_u, d_b, out=outs, concurrent=concurrent)
 
@@ -724,8 +738,9 @@ def main():
                  'slice_pairs': counts,
                  'fused_window': {'ms_per_step': ms_per_step, 'value': value, 'unit': UNIT,
                                   'wall_ms_per_step_with_barriers': wall_ms_per_step,
-                                  'what': 'every rank\'s kernels store its rows into rank 0\'s '
-                                          'peer-mapped window (this is the line\'s `value`)'},
+                                  'what': 'every rank\'s kernels store cn / union / adamic of its rows into rank 0\'s '
+                                          'peer-mapped window, rank 0 derives jaccard and pa '
+                                          '(this is the line\'s `value`)'},
                  'scoring_only': {'ms_per_step': l_ms, 'value': n_total / (l_ms * 1e-3), 'unit': UNIT,
                                   'what': 'same slices scored into local memory, nothing gathered'},
                  'nccl_gather': {'gather_ms': g_ms, 'ms_per_step': l_ms + g_ms,

@@ -8,11 +8,68 @@
 // peer-mapped address) carry each result over NVLink / NVSwitch as it is produced -- the transfer
 // rides under the computation, no SM runs a copy kernel, nothing is staged.  One process per GPU:
 // an IPC handle cannot be opened by the process that exported it.
+#include <algorithm>
 #include <cstring>
 
 #include "blp_internal.h"
 
 static_assert(sizeof(cudaIpcMemHandle_t) == BLP_IPC_HANDLE_BYTES, "handle size is part of the ABI");
+
+// The columns that are exact functions of the others and of the (replicated) graph are not sent
+// over the link at all: the destination rank derives them where they are needed.
+//   jaccard = (double)cn / (double)union   (similarity.py:108-111; IEEE division, the very
+//             expression the scoring kernels evaluate) -- 0.0 for a pair that is not in the graph
+//   pa      = deg(u) * deg(v)              ("Link prediction.R":400-415), 0 when not in the graph
+namespace blp {
+namespace {
+__global__ void k_derive(const int* __restrict__ pu, const int* __restrict__ pb, long long n, int n_users,
+                         int n_biz, const int* __restrict__ u_deg, const int* __restrict__ b_deg,
+                         const int* __restrict__ u_cn, const int* __restrict__ u_uni,
+                         const int* __restrict__ b_cn, const int* __restrict__ b_uni,
+                         double* __restrict__ u_jac, double* __restrict__ b_jac, long long* __restrict__ pa) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        if (u_jac) {
+            const int c = __ldcs(u_cn + i), u = __ldcs(u_uni + i);
+            __stcs(u_jac + i, u > 0 ? __ddiv_rn((double)c, (double)u) : 0.0);
+        }
+        if (b_jac) {
+            const int c = __ldcs(b_cn + i), u = __ldcs(b_uni + i);
+            __stcs(b_jac + i, u > 0 ? __ddiv_rn((double)c, (double)u) : 0.0);
+        }
+        if (pa) {
+            const int x = __ldcs(pu + i), y = __ldcs(pb + i);
+            long long v = 0;
+            if (x >= 0 && x < n_users && y >= 0 && y < n_biz) {
+                const int du = u_deg[x], db = b_deg[y];
+                if (du > 0 && db > 0) v = (long long)du * (long long)db;   // both ids in the graph
+            }
+            __stcs(pa + i, v);
+        }
+    }
+}
+}  // namespace
+}  // namespace blp
+
+extern "C" int blp_derive_pairs(blp_graph* g, const int32_t* pair_u, const int32_t* pair_b, int64_t n,
+                                const int32_t* u_cn, const int32_t* u_union, const int32_t* b_cn,
+                                const int32_t* b_union, double* u_jaccard, double* b_jaccard, int64_t* pa,
+                                void* stream) {
+    if (!g || n < 0 || (n > 0 && ((u_jaccard && (!u_cn || !u_union)) || (b_jaccard && (!b_cn || !b_union)) ||
+                                  (pa && (!pair_u || !pair_b))))) {
+        blp::set_error("blp_derive_pairs: bad argument");
+        return BLP_ERR_INVALID;
+    }
+    if (n == 0 || (!u_jaccard && !b_jaccard && !pa)) return BLP_OK;
+    BLP_ON_DEVICE(g->device);
+    const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)g->sm_count * 16);
+    blp::k_derive<<<blocks, 256, 0, (cudaStream_t)stream>>>(pair_u, pair_b, n, g->n_users, g->n_biz, g->u_deg,
+                                                          g->b_deg, u_cn, u_union, b_cn, b_union, u_jaccard,
+                                                          b_jaccard, (long long*)pa);
+    BLP_CUDA_TRY(cudaGetLastError());
+    return BLP_OK;
+}
 
 extern "C" int blp_peer_alloc(int device, int64_t bytes, void** dev_ptr, unsigned char* handle_out) {
     if (!dev_ptr || !handle_out || bytes <= 0) {

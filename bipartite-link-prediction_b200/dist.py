@@ -13,6 +13,11 @@ How the slices meet again on rank `dst`:
     ``blp_score_pairs`` as its output pointers, so the scoring kernels' own epilogue stores carry
     every row over NVLink / NVSwitch while the rest of the slice is still being scored: compute
     and "gather" are one kernel, no SM runs a copy, no second pass over the results.
+    Only the columns that carry information cross the link: cn, union and adamic of both sides,
+    32 of the 56 bytes per pair.  jaccard (= cn / union, the kernels' own IEEE division) and pa
+    (= deg(u) * deg(v), from the replicated degree arrays) are exact functions of those and are
+    derived on `dst` by ``blp_derive_pairs`` once the peers' rows have landed -- bit-identical to
+    what the scoring kernels write themselves.
   * ``gather_results``  (the baseline it is measured against, and what the gloo CPU test uses):
     score into local memory, then move every column slice with one grouped batch of
     point-to-point send / recv straight into place (NCCL over NVLink on the box).
@@ -31,6 +36,10 @@ import numpy as np
 REFERENCE_COLUMNS = ('u_cn', 'u_jaccard', 'u_adamic', 'b_cn', 'b_jaccard', 'b_adamic', 'pa')
 # ... plus the two union sizes (not reference outputs; tests and the roofline use them): 56 B
 ALL_COLUMNS = REFERENCE_COLUMNS + ('u_union', 'b_union')
+# what a peer's kernels store into the window (32 B per pair) ...
+WIRE_COLUMNS = ('u_cn', 'u_union', 'u_adamic', 'b_cn', 'b_union', 'b_adamic')
+# ... and what `dst` derives from them and the replicated graph
+DERIVED_COLUMNS = ('u_jaccard', 'b_jaccard', 'pa')
 _ITEMSIZE = {'cn': 4, 'union': 4, 'jaccard': 8, 'adamic': 8, 'pa': 8}
 
 
@@ -96,10 +105,13 @@ class ResultWindow(object):
     on rank `dst`, writable by the scoring kernels of every rank (see the module docstring).
 
     Collective: every rank of `group` constructs it (the IPC handle is broadcast from `dst`).
-    ``columns`` selects what is kept; a column that is left out is not computed.
+    ``columns`` selects what `dst` ends up with; a column that is left out is not computed.
+    With ``compact`` (default) the peers store only the WIRE_COLUMNS and `dst` derives
+    DERIVED_COLUMNS afterwards (``derive``); the union columns this needs are kept internally even
+    when they were not asked for.
     """
 
-    def __init__(self, graph, n_total, columns=REFERENCE_COLUMNS, dst=0, group=None):
+    def __init__(self, graph, n_total, columns=REFERENCE_COLUMNS, dst=0, group=None, compact=True):
         import torch.distributed as dist
         from . import _lib
         self._lib = _lib.load()
@@ -109,11 +121,19 @@ class ResultWindow(object):
         bad = [c for c in self.columns if c not in ALL_COLUMNS]
         if bad:
             raise ValueError('unknown result columns %r' % (bad,))
+        self.compact = bool(compact)
+        self.graph = graph
+        alloc = list(self.columns)
+        if self.compact:                         # jaccard is derived from (cn, union) on `dst`
+            for side in 'ub':
+                if side + '_jaccard' in alloc:
+                    alloc += [c for c in (side + '_cn', side + '_union') if c not in alloc]
+        self._alloc_columns = tuple(alloc)
         self.dst = dst
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.offsets, at = {}, 0
-        for c in self.columns:                      # struct of arrays, 256-byte aligned columns
+        for c in self._alloc_columns:               # struct of arrays, 256-byte aligned columns
             self.offsets[c] = at
             at += (_ITEMSIZE[_kind(c)] * max(self.n_total, 1) + 255) // 256 * 256
         self.nbytes = max(at, 256)
@@ -133,12 +153,53 @@ class ResultWindow(object):
                            'blp_peer_open')
         self.base = int(self._base.value)
 
-    def pointers(self, lo):
-        """Device addresses of row `lo` of every column, valid on THIS rank's device."""
-        return {c: self.base + self.offsets[c] + _ITEMSIZE[_kind(c)] * int(lo) for c in self.columns}
+    def written_columns(self):
+        """The columns THIS rank's kernels store: everything on `dst` (its own rows need no
+        second pass), the wire columns only on a peer of a compact window."""
+        if self._owner or not self.compact:
+            return self._alloc_columns
+        return tuple(c for c in self._alloc_columns if c not in DERIVED_COLUMNS)
+
+    def pointers(self, lo, columns=None):
+        """Device addresses of row `lo` of the columns, valid on THIS rank's device."""
+        cols = self._alloc_columns if columns is None else columns
+        return {c: self.base + self.offsets[c] + _ITEMSIZE[_kind(c)] * int(lo) for c in cols}
 
     def bytes_per_pair(self):
-        return sum(_ITEMSIZE[_kind(c)] for c in self.columns)
+        """Bytes per pair a peer sends over the link."""
+        cols = self._alloc_columns if not self.compact else \
+            tuple(c for c in self._alloc_columns if c not in DERIVED_COLUMNS)
+        return sum(_ITEMSIZE[_kind(c)] for c in cols)
+
+    def derive(self, d_all_u, d_all_b, own=(0, 0), stream=None):
+        """On `dst` of a compact window: fill DERIVED_COLUMNS for the rows the PEERS wrote, i.e.
+        all rows outside own = [lo, hi) (dst's kernels wrote every column of its own rows).
+        d_all_u / d_all_b: the whole pair list on dst's device.  Asynchronous on `stream`; the
+        caller orders it after the peers' scoring (e.g. behind a collective on the same stream)."""
+        if not (self._owner and self.compact):
+            return
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        want = [c for c in self._alloc_columns if c in DERIVED_COLUMNS]
+        if not want:
+            return
+        lo, hi = int(own[0]), int(own[1])
+        for a, b in ((0, lo), (hi, self.n_total)):
+            if b <= a:
+                continue
+            p = self.pointers(a)
+
+            def ptr(c, need):
+                return ctypes.c_void_p(p[c]) if (c in p and need) else None
+            uj, bj, pa = 'u_jaccard' in want, 'b_jaccard' in want, 'pa' in want
+            from . import _lib
+            _lib.check(self._lib.blp_derive_pairs(
+                self.graph._h, ctypes.c_void_p(d_all_u.data_ptr() + 4 * a),
+                ctypes.c_void_p(d_all_b.data_ptr() + 4 * a), b - a,
+                ptr('u_cn', uj), ptr('u_union', uj), ptr('b_cn', bj), ptr('b_union', bj),
+                ptr('u_jaccard', uj), ptr('b_jaccard', bj), ptr('pa', pa),
+                ctypes.c_void_p(stream.cuda_stream)), 'blp_derive_pairs')
 
     def tensors(self):
         """On `dst`: dict column -> torch tensor [n_total] viewing the window.  None elsewhere
@@ -176,7 +237,7 @@ def score_into_window(graph, d_u, d_b, window, lo, stream=None):
     """Score the device-resident pairs (d_u, d_b) -- rows [lo, lo+n) of the job -- with the
     window's columns as the kernels' output arrays.  Asynchronous on `stream`."""
     from . import _lib
-    ptr = window.pointers(lo)
+    ptr = window.pointers(lo, window.written_columns())
     up = {(_kind(c)): p for c, p in ptr.items() if c.startswith('u_') or c == 'pa'}
     bp = {(_kind(c)): p for c, p in ptr.items() if c.startswith('b_')}
     if up:
@@ -207,10 +268,27 @@ def score_sharded(graph, pair_u, pair_b, cost=None, dst=0, group=None, columns=R
         db = torch.from_numpy(np.ascontiguousarray(pair_b[lo:hi], dtype=np.int32)).to(graph.device)
         if hi > lo:
             score_into_window(graph, du, db, window, lo)
-        torch.cuda.synchronize(graph.device)     # this rank's rows have left for `dst`
-    if world > 1:
-        dist.barrier(group=group)                # ... and so have everybody else's
+        if world > 1:
+            rows_landed(graph, group)            # stream-ordered: behind every rank's scoring
+            if rank == dst and window.compact:
+                all_u = torch.from_numpy(np.ascontiguousarray(pair_u, dtype=np.int32)).to(graph.device)
+                all_b = torch.from_numpy(np.ascontiguousarray(pair_b, dtype=np.int32)).to(graph.device)
+                window.derive(all_u, all_b, own=(lo, hi))
+        torch.cuda.synchronize(graph.device)
     return window.tensors(), window
+
+
+def rows_landed(graph, group=None):
+    """Orders the caller's CUDA stream behind the scoring kernels of EVERY rank: a one-element
+    all-reduce issued on each rank's stream after its scoring.  A rank's stores into the peer
+    window are complete when its scoring kernels are, i.e. before its part of the collective runs,
+    so whatever `dst` enqueues after this call sees all rows.  No host synchronisation."""
+    import torch
+    import torch.distributed as dist
+    tok = getattr(graph, '_rows_token', None)
+    if tok is None:
+        tok = graph._rows_token = torch.zeros(1, dtype=torch.int32, device=graph.device)
+    dist.all_reduce(tok, group=group)
 
 
 # ------------------------------------------------------------------------------ baseline gather

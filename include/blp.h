@@ -216,6 +216,19 @@ int blp_peer_open(int device, const unsigned char* handle, void** dev_ptr);
 int blp_peer_close(int device, void* dev_ptr);
 int blp_peer_free(int device, void* dev_ptr);
 
+/*
+ * The result columns that are exact functions of the others and of the graph, computed where they
+ * are needed instead of being moved: u_jaccard / b_jaccard from (cn, union) with the scoring
+ * kernels' own expression (similarity.py:108-111; 0.0 where union is 0, i.e. the pair is not in the
+ * graph) and pa = deg(u) * deg(v) from the pair ids ("Link prediction.R":400-415).  The multi-GPU
+ * path sends only cn / union / adamic of both sides through the peer window (32 of the 56 bytes per
+ * pair) and calls this on the destination rank.  DEVICE arrays of n elements; any output may be NULL.
+ */
+int blp_derive_pairs(blp_graph* g, const int32_t* pair_u, const int32_t* pair_b, int64_t n,
+                     const int32_t* u_cn, const int32_t* u_union, const int32_t* b_cn,
+                     const int32_t* b_union, double* u_jaccard, double* b_jaccard, int64_t* pa,
+                     void* stream);
+
 /* Accounting of the most recent blp_score_pairs on this handle (per side; with
  * blp_score_pairs_host: of the last slice).  The two event times
  * are valid once that call's work has completed (the function waits for its end event). */
