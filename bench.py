@@ -622,14 +622,18 @@ def main():
     outs = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    mid_event = None      # set while diagnosing: recorded after this rank's own kernels, before the wait
+
     def step(concurrent=False, local=False):
         # the public device-resident call: both sides + pa, one side after the other on one
         # stream, so that the per-kernel event times below are those of the kernels alone
-        nonlocal outs
+        nonlocal outs, mid_event
         if window is not None and not local:
             # peers store cn / union / adamic of both sides (32 B per pair) into rank 0's window;
             # rank 0 derives jaccard and pa for their rows once every rank's kernels are done
             dmod.score_into_window(G, d_u, d_b, window, lo)
+            if mid_event is not None:
+                mid_event.record()
             dmod.rows_landed(G)
             if rank == 0:
                 window.derive(all_u, all_b, own=(lo, hi))
@@ -713,6 +717,7 @@ def main():
         barrier()
         l_ms, _, _ = timed(reps, local=True)
         barrier()
+        l_ms_own = l_ms / reps
         l_ms = reduce_max(l_ms) / reps
         counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
         keep = {k: outs[k] for k in dmod.REFERENCE_COLUMNS}
@@ -732,8 +737,26 @@ def main():
             g_tot += g0.elapsed_time(g1)
         barrier()
         g_ms = reduce_max(g_tot) / reps
+        # diagnosis: how long each rank's OWN kernels take when they store into the window (before
+        # it waits for the others), per rank
+        own_ms = []
+        for _ in range(reps):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True)
+            mid_event = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            torch.cuda.synchronize()
+            own_ms.append(e0.elapsed_time(mid_event))
+        mid_event = None
+        barrier()
+        mine = torch.tensor([statistics.mean(own_ms), l_ms_own], dtype=torch.float64, device=dev)
+        per_rank = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(per_rank, mine)
         bpp = window.bytes_per_pair()
         multi = {'bytes_per_pair_over_nvlink': bpp,
+                 'per_rank_own_kernels_ms': {'into_window': [float(t[0]) for t in per_rank],
+                                             'into_local_memory': [float(t[1]) for t in per_rank]},
                  'bytes_into_rank0_per_step': bpp * (n_total - n if rank == 0 else 0),
                  'slice_pairs': counts,
                  'fused_window': {'ms_per_step': ms_per_step, 'value': value, 'unit': UNIT,

@@ -12,6 +12,8 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, 'csrc')
 INCLUDE = os.path.join(_ROOT, 'include')
 LIB_PATH = os.path.join(_HERE, 'libblp.so')
+if os.environ.get('BLP_LIB_PATH'):        # developer override: A/B a prebuilt variant (tools/build_variants.py)
+    LIB_PATH = os.path.abspath(os.environ['BLP_LIB_PATH'])
 SOURCES = ('blp_graph.cu', 'blp_build.cu', 'blp_score.cu', 'blp_host.cu', 'blp_hop3.cu', 'blp_eval.cu',
            'blp_peer.cu')
 
@@ -25,7 +27,7 @@ EXPORTS = ('blp_version', 'blp_last_error', 'blp_device_count', 'blp_graph_creat
            'blp_score_stats', 'blp_graph_reserve_sms', 'blp_graph_create_device',
            'blp_hop3_count', 'blp_hop3_fill', 'blp_eval_precision_at_k', 'blp_eval_roc_auc',
            'blp_score_pairs_host', 'blp_peer_alloc', 'blp_peer_open', 'blp_peer_close',
-           'blp_peer_free', 'blp_derive_pairs')
+           'blp_peer_free', 'blp_derive_pairs', 'blp_peer_push')
 IPC_HANDLE_BYTES = 64
 
 
@@ -133,6 +135,7 @@ def load():
     lib.blp_peer_open.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
     lib.blp_peer_close.argtypes = [ctypes.c_int, ctypes.c_void_p]
     lib.blp_peer_free.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    lib.blp_peer_push.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.blp_derive_pairs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64] + \
         [ctypes.c_void_p] * 8
     for name in EXPORTS:

@@ -71,6 +71,47 @@ extern "C" int blp_derive_pairs(blp_graph* g, const int32_t* pair_u, const int32
     return BLP_OK;
 }
 
+// Developer diagnostic (not part of the ABI; tools/store_probe.py): SM-issued stores of `width`
+// bytes per thread, coalesced, into `dst` (typically a peer window) -- how fast can kernels push
+// results to another GPU with plain stores, alone and with every peer doing the same?
+namespace blp {
+namespace {
+template <typename T>
+__global__ void k_store_probe(T* dst, long long n, int streaming) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    T v;
+    memset(&v, 0x5a, sizeof(T));
+    for (; i < n; i += stride) {
+        if (streaming) __stcs(dst + i, v);
+        else dst[i] = v;
+    }
+}
+}  // namespace
+}  // namespace blp
+
+extern "C" int blp_debug_store_probe(void* dst, int64_t bytes, int width, int streaming, int blocks, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (width == 4) blp::k_store_probe<int><<<blocks, 256, 0, st>>>((int*)dst, bytes / 4, streaming);
+    else if (width == 8) blp::k_store_probe<double><<<blocks, 256, 0, st>>>((double*)dst, bytes / 8, streaming);
+    else if (width == 16) blp::k_store_probe<int4><<<blocks, 256, 0, st>>>((int4*)dst, bytes / 16, streaming);
+    else return BLP_ERR_INVALID;
+    BLP_CUDA_TRY(cudaGetLastError());
+    return BLP_OK;
+}
+
+extern "C" int blp_peer_push(int device, void* dst, const void* src, int64_t bytes, void* stream) {
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) {
+        blp::set_error("blp_peer_push: bad argument");
+        return BLP_ERR_INVALID;
+    }
+    if (bytes == 0) return BLP_OK;
+    BLP_ON_DEVICE(device);
+    // a copy-engine transfer: no SM is involved, so it runs beside the scoring kernels
+    BLP_CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return BLP_OK;
+}
+
 extern "C" int blp_peer_alloc(int device, int64_t bytes, void** dev_ptr, unsigned char* handle_out) {
     if (!dev_ptr || !handle_out || bytes <= 0) {
         blp::set_error("blp_peer_alloc: bad argument");

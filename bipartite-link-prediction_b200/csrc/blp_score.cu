@@ -37,6 +37,10 @@
 
 #include "blp_internal.h"
 
+#ifndef BLP_HUB_TMA
+#define BLP_HUB_TMA 1   // 0: A/B build with the cp.async hub copy (and no async-proxy fences)
+#endif
+
 #include "blp_score_common.cuh"
 #include "blp_score_group.cuh"
 #include "blp_score_light.cuh"
@@ -383,9 +387,7 @@ __device__ unsigned long long g_phase_cycles[16];
 #ifndef BLP_THREADS_PER_SM
 #define BLP_THREADS_PER_SM 1024
 #endif
-#ifndef BLP_HUB_TMA
-#define BLP_HUB_TMA 1   // 0: A/B build with the cp.async hub copy
-#endif
+
 
 // Descriptor of one work item (group) as the kernel carries it in registers.  The uniform part
 // of the chain  item -> node -> (pair range, row)  is fetched for the NEXT group in two stages
@@ -458,7 +460,9 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
         const int n4 = a.bm_words >> 2;
         for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+#if BLP_HUB_TMA
     fence_async_smem();   // the clear (and the barrier's init) before any bulk copy into the bitmap
+#endif
     __syncthreads();
     GroupRegs cur;
     cur.item = ts.item_next;
@@ -742,7 +746,9 @@ __global__ void __launch_bounds__(NT, (BLP_THREADS_PER_SM / NT) > 0 ? (BLP_THREA
             uint4* b4 = reinterpret_cast<uint4*>(bm);
             const int n4 = a.bm_words >> 2;
             for (int i = tid; i < n4; i += NT) b4[i] = make_uint4(0u, 0u, 0u, 0u);
+#if BLP_HUB_TMA
             fence_async_smem();   // ... before the next group's bulk copy may land on these words
+#endif
         }
         }   // id-range passes
         if (tid == 0) {   // ordered before the next group's counting by its barriers

@@ -153,6 +153,22 @@ class ResultWindow(object):
                            'blp_peer_open')
         self.base = int(self._base.value)
 
+    def _staging(self, n, kinds):
+        """Local staging of a peer's business-side columns (kept until the next call)."""
+        import torch
+        dt = {'cn': torch.int32, 'union': torch.int32, 'jaccard': torch.float64,
+              'adamic': torch.float64}
+        st = getattr(self, '_stage', None)
+        if st is None or any(k not in st or st[k].numel() != n for k in kinds):
+            st = self._stage = {k: torch.empty(n, dtype=dt[k], device=self.device) for k in kinds}
+        return {k: st[k] for k in kinds}
+
+    def _push_stream(self):
+        import torch
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def written_columns(self):
         """The columns THIS rank's kernels store: everything on `dst` (its own rows need no
         second pass), the wire columns only on a peer of a compact window."""
@@ -234,16 +250,46 @@ class ResultWindow(object):
 
 
 def score_into_window(graph, d_u, d_b, window, lo, stream=None):
-    """Score the device-resident pairs (d_u, d_b) -- rows [lo, lo+n) of the job -- with the
-    window's columns as the kernels' output arrays.  Asynchronous on `stream`."""
+    """Score the device-resident pairs (d_u, d_b) -- rows [lo, lo+n) of the job -- into the window.
+    Asynchronous on `stream`.
+
+    On the window's owner both sides write their rows in place.  On a peer:
+      * the USER side (the long one) runs with the window's columns as its output arrays: the
+        scoring kernels' own epilogue stores carry the rows over NVLink while the kernels run;
+      * the BUSINESS side runs first, into local staging: its results appear in one burst (the
+        un-permute pass writes every column in a fraction of a millisecond), which seven peers
+        cannot push through one GPU's NVLink ingress at once without stalling -- so its columns
+        go over by copy engine (``blp_peer_push``) on a side stream, under the user-side kernels.
+    """
+    import torch
     from . import _lib
-    ptr = window.pointers(lo, window.written_columns())
+    if stream is None:
+        stream = torch.cuda.current_stream(graph.device)
+    cols = window.written_columns()
+    ptr = window.pointers(lo, cols)
     up = {(_kind(c)): p for c, p in ptr.items() if c.startswith('u_') or c == 'pa'}
     bp = {(_kind(c)): p for c, p in ptr.items() if c.startswith('b_')}
+    n = int(d_u.numel())
+    if window._owner or window.world == 1 or not bp or n == 0:
+        if up:
+            graph.score_side(_lib.SIDE_USER, d_u, d_b, want=(), out_ptr=up, stream=stream)
+        if bp:
+            graph.score_side(_lib.SIDE_BUSINESS, d_u, d_b, want=(), out_ptr=bp, stream=stream)
+        return
+    stage = window._staging(n, sorted(bp))
+    graph.score_side(_lib.SIDE_BUSINESS, d_u, d_b, want=tuple(sorted(bp)), out=stage, stream=stream)
+    side = window._push_stream()
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    side.wait_event(ev)
+    dev = graph.device.index or 0
+    for k in sorted(bp):
+        _lib.check(window._lib.blp_peer_push(dev, ctypes.c_void_p(bp[k]), ctypes.c_void_p(stage[k].data_ptr()),
+                                             stage[k].numel() * stage[k].element_size(),
+                                             ctypes.c_void_p(side.cuda_stream)), 'blp_peer_push')
     if up:
         graph.score_side(_lib.SIDE_USER, d_u, d_b, want=(), out_ptr=up, stream=stream)
-    if bp:
-        graph.score_side(_lib.SIDE_BUSINESS, d_u, d_b, want=(), out_ptr=bp, stream=stream)
+    stream.wait_stream(side)
 
 
 def score_sharded(graph, pair_u, pair_b, cost=None, dst=0, group=None, columns=REFERENCE_COLUMNS,

@@ -215,6 +215,12 @@ int blp_peer_alloc(int device, int64_t bytes, void** dev_ptr, unsigned char* han
 int blp_peer_open(int device, const unsigned char* handle, void** dev_ptr);
 int blp_peer_close(int device, void* dev_ptr);
 int blp_peer_free(int device, void* dev_ptr);
+/* Copy-engine transfer of `bytes` from local device memory into a (peer) window, asynchronous on
+ * `stream` (a cudaStream_t of `device`): for results that are produced in one burst -- the
+ * business side's un-permute pass writes its columns in a fraction of a millisecond, which seven
+ * peers cannot push through one GPU's NVLink ingress at once -- so that the transfer rides on a
+ * side stream under the next kernels instead of stalling the stores of this one. */
+int blp_peer_push(int device, void* dst, const void* src, int64_t bytes, void* stream);
 
 /*
  * The result columns that are exact functions of the others and of the graph, computed where they
