@@ -1,12 +1,10 @@
 set -x
 cd $GRAFT_REPO_ROOT
-N=$(nvidia-smi -L | wc -l)
-timeout 600 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -4
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29548 bench.py --gpus $N --steps 10 --warmup 3 --no-other-configs > gpurun_out/c12_bench_n$N.json 2> gpurun_out/c12_bench_n$N.err; echo "bench rc $?"; tail -c 600 gpurun_out/c12_bench_n$N.err
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29549 bench.py --gpus 2 --config C5 --steps 3 --warmup 3 --quick --no-cpu-baseline > gpurun_out/c14_bench_c5_n2.json 2> gpurun_out/c14_bench_c5_n2.err; echo "bench rc $?"; tail -c 1500 gpurun_out/c14_bench_c5_n2.err
 python - <<PY
 import json
 try:
-    d=json.loads(open('gpurun_out/c12_bench_n$N.json').read().strip().splitlines()[-1])
-    m=d['multi_gpu']; print('N=$N value', d['value'], 'ms', d['ms_per_step']); print(json.dumps(m['per_rank_own_kernels_ms'])); print(m['fused_window']['ms_per_step'], m['scoring_only']['ms_per_step'], m['nccl_gather']['ms_per_step'], m['all_rows_match_unsharded_call'], m['nccl_gather_rows_match'], m['oracle_check']['ok'])
+    d=json.loads(open('gpurun_out/c14_bench_c5_n2.json').read().strip().splitlines()[-1])
+    print('C5 N=2 value', d['value'], 'ms', d['ms_per_step']); print(json.dumps(d['multi_gpu'])[:1500]); r=d['roofline']; print(r['frac'], r['kernel_ms'], r['business_kernel']['kernel_ms'], r['launch'])
 except Exception as e: print('no json', e)
 PY
