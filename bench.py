@@ -394,6 +394,7 @@ def other_config_line(name, n_pairs, steps, rank, world, dev, cores, peak):
         if rank == 0:
             keep = torch.cat([torch.arange(c, device=dev) + r * longest for r, c in enumerate(counts)])
             all_u, all_b = g_u[keep].contiguous(), g_b[keep].contiguous()
+            window.attach_pairs(all_u, all_b, (lo, lo + n))
         del g_u, g_b, pad_u, pad_b
 
     tot, ku, kb = 0.0, [], []
@@ -405,7 +406,7 @@ def other_config_line(name, n_pairs, steps, rank, world, dev, cores, peak):
         if world > 1:
             dmod.rows_landed(G)
             if rank == 0:
-                window.derive(all_u, all_b, own=(lo, lo + n))
+                window.derive()
         e1.record()
         e1.synchronize()
         if it >= 3:
@@ -615,6 +616,8 @@ def main():
         if rank != 0:
             del all_u, all_b
         window = dmod.ResultWindow(G, n_total, columns=dmod.REFERENCE_COLUMNS, dst=0)
+        if rank == 0:
+            window.attach_pairs(all_u, all_b, (lo, hi))
     else:
         d_u = torch.from_numpy(pu).to(dev)
         d_b = torch.from_numpy(pv).to(dev)
@@ -636,7 +639,7 @@ def main():
                 mid_event.record()
             dmod.rows_landed(G)
             if rank == 0:
-                window.derive(all_u, all_b, own=(lo, hi))
+                window.derive()        # jaccard of the peers' rows (their pa was derived under the scoring)
         else:
             outs = G.score_pairs(d_u, d_b, out=outs, concurrent=concurrent)
 

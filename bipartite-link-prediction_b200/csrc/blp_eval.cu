@@ -30,6 +30,15 @@ long long current_sm_count() {
 
 constexpr unsigned kEvalAll = 0xffffffffu;
 
+// eval.py:21-24 sorts a user's pairs by score (descending, stable) and averages the labels of the
+// first min(k, len).  An element's place in that order is #larger + #equal-in-front; "a before b"
+// <=> score(a) > score(b) or (equal and index(a) < index(b)).  One warp per user.
+//   len <= kPrecQuadratic : every element counts the elements before it (len^2 / 32 steps)
+//   longer lists (hop-3 candidate sets run to thousands): the first n = min(k, len) places are
+//   found by n rounds of a warp arg-best over the elements that come after the previous pick --
+//   n * len / 32 steps instead of len^2 / 32
+constexpr int kPrecQuadratic = 96;
+
 __global__ void k_precision_at_k(const long long* __restrict__ off, const int* __restrict__ labels,
                                  const double* __restrict__ scores, long long n_groups, int k,
                                  double* __restrict__ prec) {
@@ -41,14 +50,43 @@ __global__ void k_precision_at_k(const long long* __restrict__ off, const int* _
         const int len = (int)(off[g + 1] - lo);
         const int n = min(k, len);
         int hits = 0;
-        for (int i = lane; i < len; i += 32) {
-            const double pi = scores[lo + i];
-            int pos = 0;
-            for (int j = 0; j < len; ++j) {
-                const double pj = scores[lo + j];
-                pos += (pj > pi) || (pj == pi && j < i);
+        if (len <= kPrecQuadratic) {
+            for (int i = lane; i < len; i += 32) {
+                const double pi = scores[lo + i];
+                int pos = 0;
+                for (int j = 0; j < len; ++j) {
+                    const double pj = scores[lo + j];
+                    pos += (pj > pi) || (pj == pi && j < i);
+                }
+                if (pos < n) hits += labels[lo + i];
             }
-            if (pos < n) hits += labels[lo + i];
+        } else {
+            double prev_s = 0.0;
+            int prev_i = -1;
+            for (int r = 0; r < n; ++r) {
+                double best_s = 0.0;
+                int best_i = -1;
+                for (int i = lane; i < len; i += 32) {
+                    const double s = scores[lo + i];
+                    const bool after = r == 0 || s < prev_s || (s == prev_s && i > prev_i);
+                    if (after && (best_i < 0 || s > best_s || (s == best_s && i < best_i))) {
+                        best_s = s;
+                        best_i = i;
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {   // butterfly: every lane ends with the same pick
+                    const double os = __shfl_xor_sync(kEvalAll, best_s, d);
+                    const int oi = __shfl_xor_sync(kEvalAll, best_i, d);
+                    if (oi >= 0 && (best_i < 0 || os > best_s || (os == best_s && oi < best_i))) {
+                        best_s = os;
+                        best_i = oi;
+                    }
+                }
+                prev_s = best_s;
+                prev_i = best_i;
+                if (lane == 0 && best_i >= 0) hits += labels[lo + best_i];
+            }
         }
         hits = __reduce_add_sync(kEvalAll, hits);
         if (lane == 0) prec[g] = n > 0 ? (double)hits / (double)n : 0.0;

@@ -187,17 +187,35 @@ class ResultWindow(object):
             tuple(c for c in self._alloc_columns if c not in DERIVED_COLUMNS)
         return sum(_ITEMSIZE[_kind(c)] for c in cols)
 
-    def derive(self, d_all_u, d_all_b, own=(0, 0), stream=None):
-        """On `dst` of a compact window: fill DERIVED_COLUMNS for the rows the PEERS wrote, i.e.
-        all rows outside own = [lo, hi) (dst's kernels wrote every column of its own rows).
-        d_all_u / d_all_b: the whole pair list on dst's device.  Asynchronous on `stream`; the
-        caller orders it after the peers' scoring (e.g. behind a collective on the same stream)."""
+    def attach_pairs(self, d_all_u, d_all_b, own):
+        """On `dst`: the whole pair list on its device and its own row range [lo, hi).  With the
+        pairs attached, ``score_into_window`` derives pa for the peers' rows (a function of the
+        pair ids alone) on a side stream under dst's own scoring kernels, and ``derive`` with no
+        arguments fills what is left once the peers' rows have landed."""
+        self._pairs = (d_all_u, d_all_b, (int(own[0]), int(own[1])))
+        self._early = ()
+
+    def derive(self, d_all_u=None, d_all_b=None, own=None, stream=None, which=None):
+        """On `dst` of a compact window: fill DERIVED_COLUMNS (or the subset `which`) for the rows
+        the PEERS wrote, i.e. all rows outside own = [lo, hi) (dst's kernels wrote every column
+        of its own rows).  d_all_u / d_all_b: the whole pair list on dst's device (default: what
+        attach_pairs was given; then the columns already derived early are skipped).
+        Asynchronous on `stream`; the caller orders it after the peers' scoring (e.g. behind a
+        collective on the same stream, ``rows_landed``)."""
         if not (self._owner and self.compact):
             return
         import torch
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
-        want = [c for c in self._alloc_columns if c in DERIVED_COLUMNS]
+        skip = ()
+        if d_all_u is None:
+            if getattr(self, '_pairs', None) is None:
+                raise ValueError('derive() needs the pair list (pass it or call attach_pairs)')
+            d_all_u, d_all_b, own = self._pairs
+            if which is None:
+                skip = self._early
+        want = [c for c in self._alloc_columns if c in DERIVED_COLUMNS and c not in skip and
+                (which is None or c in which)]
         if not want:
             return
         lo, hi = int(own[0]), int(own[1])
@@ -271,10 +289,20 @@ def score_into_window(graph, d_u, d_b, window, lo, stream=None):
     bp = {(_kind(c)): p for c, p in ptr.items() if c.startswith('b_')}
     n = int(d_u.numel())
     if window._owner or window.world == 1 or not bp or n == 0:
-        if up:
+        early = window._owner and window.world > 1 and getattr(window, '_pairs', None) is not None
+        if early:
+            # pa of the peers' rows depends on the pair ids alone: derived now, on the side
+            # stream, under this rank's own scoring kernels
+            side = window._push_stream()
+            side.wait_stream(stream)
+            window.derive(*window._pairs, stream=side, which=('pa',))
+            window._early = ('pa',)
+        if up and n:
             graph.score_side(_lib.SIDE_USER, d_u, d_b, want=(), out_ptr=up, stream=stream)
-        if bp:
+        if bp and n:
             graph.score_side(_lib.SIDE_BUSINESS, d_u, d_b, want=(), out_ptr=bp, stream=stream)
+        if early:
+            stream.wait_stream(side)
         return
     stage = window._staging(n, sorted(bp))
     graph.score_side(_lib.SIDE_BUSINESS, d_u, d_b, want=tuple(sorted(bp)), out=stage, stream=stream)
@@ -312,14 +340,15 @@ def score_sharded(graph, pair_u, pair_b, cost=None, dst=0, group=None, columns=R
     with torch.cuda.device(graph.device):
         du = torch.from_numpy(np.ascontiguousarray(pair_u[lo:hi], dtype=np.int32)).to(graph.device)
         db = torch.from_numpy(np.ascontiguousarray(pair_b[lo:hi], dtype=np.int32)).to(graph.device)
-        if hi > lo:
-            score_into_window(graph, du, db, window, lo)
+        if world > 1 and rank == dst and window.compact:
+            all_u = torch.from_numpy(np.ascontiguousarray(pair_u, dtype=np.int32)).to(graph.device)
+            all_b = torch.from_numpy(np.ascontiguousarray(pair_b, dtype=np.int32)).to(graph.device)
+            window.attach_pairs(all_u, all_b, (lo, hi))
+        score_into_window(graph, du, db, window, lo)
         if world > 1:
             rows_landed(graph, group)            # stream-ordered: behind every rank's scoring
             if rank == dst and window.compact:
-                all_u = torch.from_numpy(np.ascontiguousarray(pair_u, dtype=np.int32)).to(graph.device)
-                all_b = torch.from_numpy(np.ascontiguousarray(pair_b, dtype=np.int32)).to(graph.device)
-                window.derive(all_u, all_b, own=(lo, hi))
+                window.derive()
         torch.cuda.synchronize(graph.device)
     return window.tensors(), window
 

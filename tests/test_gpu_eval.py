@@ -26,6 +26,8 @@ def _case(seed, n_users, k_lo, k_hi, kind):
 
 @pytest.mark.parametrize('seed,n_users,k_lo,k_hi,kind', [
     (0, 300, 1, 40, 'int'), (1, 200, 5, 90, 'mixed'), (2, 50, 200, 700, 'float'), (3, 1, 3, 3, 'int'),
+    # long lists take the top-k selection path of k_precision_at_k: heavy ties, int 0 mixed with floats
+    (4, 30, 150, 400, 'int'), (5, 20, 97, 300, 'mixed'),
 ])
 def test_metrics_match_eval_py(mods, seed, n_users, k_lo, k_hi, kind):
     from oracle import eval_oracle
