@@ -27,7 +27,8 @@ EXPORTS = ('blp_version', 'blp_last_error', 'blp_device_count', 'blp_graph_creat
            'blp_score_stats', 'blp_graph_reserve_sms', 'blp_graph_create_device',
            'blp_hop3_count', 'blp_hop3_fill', 'blp_eval_precision_at_k', 'blp_eval_roc_auc',
            'blp_score_pairs_host', 'blp_peer_alloc', 'blp_peer_open', 'blp_peer_close',
-           'blp_peer_free', 'blp_derive_pairs', 'blp_peer_push')
+           'blp_peer_free', 'blp_derive_pairs', 'blp_peer_push', 'blp_edge_list_count',
+           'blp_edge_list_parse')
 IPC_HANDLE_BYTES = 64
 
 
@@ -135,6 +136,9 @@ def load():
     lib.blp_peer_open.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
     lib.blp_peer_close.argtypes = [ctypes.c_int, ctypes.c_void_p]
     lib.blp_peer_free.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    lib.blp_edge_list_count.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p]
+    lib.blp_edge_list_parse.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                        ctypes.c_void_p]
     lib.blp_peer_push.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.blp_derive_pairs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64] + \
         [ctypes.c_void_p] * 8

@@ -404,6 +404,124 @@ int radix_sort_u64(unsigned long long* keys, unsigned long long* tmp, long long 
     *sorted = keys;
     return rc;
 }
+// ------------------------------------------------------------------------------------ graph.txt
+// The text of graph.txt -- one "<user_id> <business_id>\n" per review (dataset_maker.py:197) -- is
+// parsed where it will be used: the file's bytes go to the device as they are, a first pass
+// counts the data lines of every 4 KB tile, a scan turns the counts into line numbers, and a
+// second pass lets the thread that owns a line's first byte parse columns 0 and 1 (what
+// snap.LoadEdgeList(PUNGraph, file, 0, 1) reads, similarity.py:16).  A data line is a line whose
+// first non-blank character starts an integer; blank lines and comment lines are skipped, further
+// columns ignored, "\r\n" accepted.
+namespace {
+constexpr int kParseTile = 4096;   // bytes per CTA: 256 threads x 16
+
+__device__ __forceinline__ bool parse_blank(char c) { return c == ' ' || c == '\t' || c == '\r'; }
+__device__ __forceinline__ bool parse_digit(char c) { return c >= '0' && c <= '9'; }
+
+__device__ __forceinline__ bool data_line_at(const char* __restrict__ t, long long n, long long i) {
+    if (i > 0 && t[i - 1] != '\n') return false;
+    long long j = i;
+    while (j < n && parse_blank(t[j])) ++j;
+    if (j >= n) return false;
+    const char c = t[j];
+    if (c == '-' || c == '+') return j + 1 < n && parse_digit(t[j + 1]);
+    return parse_digit(c);
+}
+
+// one whitespace-separated integer starting at or after j (never crosses the line's end)
+__device__ __forceinline__ bool parse_int(const char* __restrict__ t, long long n, long long& j, long long& out) {
+    while (j < n && parse_blank(t[j])) ++j;
+    if (j >= n) return false;
+    bool neg = false;
+    if (t[j] == '-' || t[j] == '+') {
+        neg = t[j] == '-';
+        ++j;
+    }
+    if (j >= n || !parse_digit(t[j])) return false;
+    long long v = 0;
+    while (j < n && parse_digit(t[j])) {
+        v = v * 10 + (t[j] - '0');
+        ++j;
+    }
+    out = neg ? -v : v;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_parse_count(const char* __restrict__ t, long long n,
+                                                     unsigned* __restrict__ tile_cnt) {
+    __shared__ unsigned s_w[8];
+    const long long lo = (long long)blockIdx.x * kParseTile + threadIdx.x * 16;
+    unsigned c = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (lo + j < n) c += data_line_at(t, n, lo + j) ? 1u : 0u;
+    c = __reduce_add_sync(kFullMask, c);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int w = 0; w < 8; ++w) tot += s_w[w];
+        tile_cnt[blockIdx.x] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_parse_lines(const char* __restrict__ t, long long n,
+                                                     const unsigned long long* __restrict__ tile_base,
+                                                     long long n_lines, long long* __restrict__ col0,
+                                                     long long* __restrict__ col1,
+                                                     unsigned long long* __restrict__ bad_line) {
+    __shared__ unsigned s_w[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long lo = (long long)blockIdx.x * kParseTile + threadIdx.x * 16;
+    unsigned mask = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (lo + j < n && data_line_at(t, n, lo + j)) mask |= 1u << j;
+    const unsigned c = __popc(mask);
+    unsigned inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned v = __shfl_up_sync(kFullMask, inc, d);
+        if (lane >= d) inc += v;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    unsigned long long line = tile_base[blockIdx.x] + inc - c;
+    for (int w = 0; w < warp; ++w) line += s_w[w];
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        long long at = lo + j, a = 0, b = 0;
+        const bool ok = parse_int(t, n, at, a) && parse_int(t, n, at, b);
+        if ((long long)line < n_lines) {
+            col0[line] = a;
+            col1[line] = b;
+        }
+        if (!ok) atomicMin(bad_line, line);
+        ++line;
+    }
+}
+
+int parse_tile_counts(const char* text, long long n_bytes, cudaStream_t st, unsigned** tile_cnt_out, int* n_tiles_out) {
+    const long long n_tiles = (n_bytes + kParseTile - 1) / kParseTile;
+    if (n_tiles >= (1LL << 31)) {
+        set_error("edge list text too large (more than 8 TB)");
+        return BLP_ERR_UNSUPPORTED;
+    }
+    unsigned* tile_cnt = nullptr;
+    BLP_CUDA_TRY(scratch_alloc((void**)&tile_cnt, sizeof(unsigned) * (size_t)std::max<long long>(n_tiles, 1), st));
+    if (n_tiles > 0) k_parse_count<<<(unsigned)n_tiles, 256, 0, st>>>(text, n_bytes, tile_cnt);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaFreeAsync(tile_cnt, st);
+        return cuda_fail(e, "k_parse_count", __FILE__, __LINE__);
+    }
+    *tile_cnt_out = tile_cnt;
+    *n_tiles_out = (int)n_tiles;
+    return BLP_OK;
+}
+}  // namespace
+
 // ------------------------------------------------------------------------------------ id ranges
 // One warp per row of a ranged side's middle adjacency: count the ids of every id range, write the
 // exclusive prefix to seg_off[row][0..R] and -- unless the row is known to ascend already -- move
@@ -489,6 +607,81 @@ int build_range_segments(blp_graph* g, bool reorder, int* tmp, cudaStream_t st) 
 }
 
 }  // namespace blp
+
+extern "C" int blp_edge_list_count(const char* text_dev, int64_t n_bytes, int64_t* n_lines_host, void* stream) {
+    using namespace blp;
+    if (!n_lines_host || n_bytes < 0 || (n_bytes > 0 && !text_dev)) {
+        set_error("blp_edge_list_count: bad argument");
+        return BLP_ERR_INVALID;
+    }
+    *n_lines_host = 0;
+    if (n_bytes == 0) return BLP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* tile_cnt = nullptr;
+    int n_tiles = 0;
+    int rc = parse_tile_counts(text_dev, n_bytes, st, &tile_cnt, &n_tiles);
+    if (rc != BLP_OK) return rc;
+    Scanner scan;
+    scan.st = st;
+    unsigned long long* base = nullptr;
+    unsigned long long total = 0;
+    cudaError_t e = scratch_alloc((void**)&base, sizeof(unsigned long long) * (size_t)n_tiles, st);
+    if (e == cudaSuccess) rc = scan.run(tile_cnt, n_tiles, false, base, &total);
+    scan.release();
+    cudaFreeAsync(tile_cnt, st);
+    if (base) cudaFreeAsync(base, st);
+    if (e != cudaSuccess) return cuda_fail(e, "scratch_alloc", __FILE__, __LINE__);
+    if (rc != BLP_OK) return rc;
+    *n_lines_host = (int64_t)total;
+    return BLP_OK;
+}
+
+extern "C" int blp_edge_list_parse(const char* text_dev, int64_t n_bytes, int64_t n_lines, int64_t* col0_dev,
+                                   int64_t* col1_dev, void* stream) {
+    using namespace blp;
+    if (n_bytes < 0 || n_lines < 0 || (n_bytes > 0 && !text_dev) || (n_lines > 0 && (!col0_dev || !col1_dev))) {
+        set_error("blp_edge_list_parse: bad argument");
+        return BLP_ERR_INVALID;
+    }
+    if (n_bytes == 0 || n_lines == 0) return BLP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned* tile_cnt = nullptr;
+    int n_tiles = 0;
+    int rc = parse_tile_counts(text_dev, n_bytes, st, &tile_cnt, &n_tiles);
+    if (rc != BLP_OK) return rc;
+    Scanner scan;
+    scan.st = st;
+    unsigned long long *base = nullptr, *bad = nullptr;
+    unsigned long long total = 0, bad_host = ~0ull;
+    cudaError_t e = scratch_alloc((void**)&base, sizeof(unsigned long long) * (size_t)n_tiles, st);
+    if (e == cudaSuccess) e = scratch_alloc((void**)&bad, sizeof(unsigned long long), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bad, &bad_host, sizeof(bad_host), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) rc = scan.run(tile_cnt, n_tiles, false, base, &total);
+    if (e == cudaSuccess && rc == BLP_OK && (int64_t)total == n_lines) {
+        k_parse_lines<<<(unsigned)n_tiles, 256, 0, st>>>(text_dev, n_bytes, base, n_lines, (long long*)col0_dev,
+                                                        (long long*)col1_dev, bad);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&bad_host, bad, sizeof(bad_host), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    scan.release();
+    cudaFreeAsync(tile_cnt, st);
+    if (base) cudaFreeAsync(base, st);
+    if (bad) cudaFreeAsync(bad, st);
+    if (e != cudaSuccess) return cuda_fail(e, "blp_edge_list_parse", __FILE__, __LINE__);
+    if (rc != BLP_OK) return rc;
+    if ((int64_t)total != n_lines) {
+        set_error("blp_edge_list_parse: n_lines does not match blp_edge_list_count of this text");
+        return BLP_ERR_INVALID;
+    }
+    if (bad_host != ~0ull) {
+        char buf[128];
+        snprintf(buf, sizeof(buf), "blp_edge_list_parse: data line %llu has fewer than two integer columns", bad_host);
+        set_error(buf);
+        return BLP_ERR_INVALID;
+    }
+    return BLP_OK;
+}
 
 extern "C" int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n_edges,
                                        const int32_t* edge_u_dev, const int32_t* edge_b_dev,

@@ -35,6 +35,31 @@ def read_edge_list(path):
         return arr[:, 0].copy(), arr[:, 1].copy()
 
 
+def read_edge_list_device(path, device=None):
+    """graph.txt -> two int64 CUDA tensors, parsed ON the device (``blp_edge_list_count`` /
+    ``blp_edge_list_parse``): the file's bytes are uploaded as they are; data lines are lines
+    whose first non-blank character starts an integer (blank / comment lines skipped, columns
+    beyond the second ignored).  Raises ValueError when a data line lacks a second integer."""
+    lib = _lib.load()
+    if device is None:
+        device = torch.cuda.current_device()
+    dev = device if isinstance(device, torch.device) else torch.device('cuda', int(device))
+    raw = np.fromfile(path, dtype=np.uint8)
+    with torch.cuda.device(dev):
+        text = torch.from_numpy(raw).to(dev)
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        n_lines = ctypes.c_int64(0)
+        _lib.check(lib.blp_edge_list_count(ctypes.c_void_p(text.data_ptr()), int(text.numel()),
+                                           ctypes.byref(n_lines), st), 'blp_edge_list_count')
+        n = int(n_lines.value)
+        col0 = torch.empty(n, dtype=torch.int64, device=dev)
+        col1 = torch.empty(n, dtype=torch.int64, device=dev)
+        _lib.check(lib.blp_edge_list_parse(ctypes.c_void_p(text.data_ptr()), int(text.numel()), n,
+                                           ctypes.c_void_p(col0.data_ptr()),
+                                           ctypes.c_void_p(col1.data_ptr()), st), 'blp_edge_list_parse')
+    return col0, col1
+
+
 class _NodeIt(object):
     """``G.GetNI(i)`` -- only ``GetDeg`` / ``GetId`` are used by the reference (similarity.py:22,121)."""
 
@@ -124,9 +149,36 @@ class BipartiteGraph(object):
                    build=build)
 
     @classmethod
-    def from_edge_list(cls, path, src_col=0, dst_col=1, device=None):
+    def from_id_edges_device(cls, ids_u, ids_b, device=None):
+        """The same for int64 CUDA tensors of shared-space ids: compaction (sorted id tables +
+        inverse) and the disjointness check run on the device, the graph is built by
+        ``blp_graph_create_device`` -- nothing but the two id tables visits the host."""
+        dev = ids_u.device
+        if ids_u.numel() == 0:
+            raise ValueError('empty edge list')
+        with torch.cuda.device(dev):
+            users, eu = torch.unique(ids_u, return_inverse=True)
+            bizs, eb = torch.unique(ids_b, return_inverse=True)
+            pos = torch.searchsorted(bizs, users).clamp_(max=bizs.numel() - 1)
+            if bool((bizs[pos] == users).any()):
+                raise ValueError('graph is not bipartite by column: some id appears both as a user '
+                                 '(column 0) and as a business (column 1)')
+            return cls(int(users.numel()), int(bizs.numel()), eu.to(torch.int32), eb.to(torch.int32),
+                       device=dev, user_ids=users.cpu().numpy(), biz_ids=bizs.cpu().numpy(),
+                       build='device')
+
+    @classmethod
+    def from_edge_list(cls, path, src_col=0, dst_col=1, device=None, parse='device'):
+        """``snap.LoadEdgeList(snap.PUNGraph, path, 0, 1)`` (similarity.py:16).  parse='device'
+        (default): the text is parsed, compacted and turned into the CSR pair on the GPU;
+        parse='host': pandas' C parser + the host-side compaction (same graph)."""
         if (src_col, dst_col) != (0, 1):
             raise ValueError('column 0 must hold users and column 1 businesses')
+        if parse == 'device':
+            u, b = read_edge_list_device(path, device)
+            return cls.from_id_edges_device(u, b, device=device)
+        if parse != 'host':
+            raise ValueError("parse must be 'device' or 'host'")
         u, b = read_edge_list(path)
         return cls.from_id_edges(u, b, device=device)
 

@@ -113,6 +113,21 @@ int blp_graph_create(int32_t n_users, int32_t n_biz, int64_t n_edges,
 int blp_graph_create_device(int32_t n_users, int32_t n_biz, int64_t n_edges,
                             const int32_t* edge_u_dev, const int32_t* edge_b_dev,
                             int device, void* stream, blp_graph** out);
+/*
+ * graph.txt on the device (parse -> sort -> de-dup).  `text_dev` holds
+ * the file's bytes in DEVICE memory: one "<user_id> <business_id>\n" per review
+ * (dataset_maker.py:197).  A data line is a line whose first non-blank character starts an
+ * integer; blank and comment lines are skipped, columns beyond the second ignored (what
+ * snap.LoadEdgeList(PUNGraph, file, 0, 1) reads, similarity.py:16).
+ *   blp_edge_list_count : *n_lines_host = number of data lines
+ *   blp_edge_list_parse : col0_dev / col1_dev (DEVICE, n_lines x int64) = the ids of columns 0 / 1
+ *                         in file order; BLP_ERR_INVALID when a data line lacks a second integer
+ * Both run on the caller's current device and return when done.  The ids are of the reference's
+ * shared id space; the host layer compacts them to local indices for blp_graph_create_device.
+ */
+int blp_edge_list_count(const char* text_dev, int64_t n_bytes, int64_t* n_lines_host, void* stream);
+int blp_edge_list_parse(const char* text_dev, int64_t n_bytes, int64_t n_lines, int64_t* col0_dev,
+                        int64_t* col1_dev, void* stream);
 int blp_graph_destroy(blp_graph* g);
 int blp_graph_info(const blp_graph* g, blp_graph_info_t* info);
 

@@ -81,3 +81,50 @@ def test_device_build_c2_and_timing(mods):
     b = Gd.score_pairs_host(pu, pv)
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_edge_list_text_parsed_on_the_device(mods, tmp_path):
+    """graph.txt parsed by blp_edge_list_count / blp_edge_list_parse == the host parser, on the
+    format dataset_maker.py:197 writes and on the oddities a text file can carry."""
+    import torch
+    graph, synth = mods
+    util = pkg('util')
+    # (1) a real-shaped file: one "<u> <b>\n" per review, duplicates included
+    eu, eb = synth.make_graph(3000, 400, 20_000, seed=41, shift_u=2.0, shift_b=2.0)
+    ids_u, ids_b = synth.shared_ids(3000, eu, eb)
+    path = str(tmp_path / 'graph.txt')
+    util.write_edge_list(path, ids_u, ids_b)
+    hu, hb = graph.read_edge_list(path)
+    du, db = graph.read_edge_list_device(path)
+    assert torch.equal(du.cpu(), torch.from_numpy(hu)) and torch.equal(db.cpu(), torch.from_numpy(hb))
+    # (2) oddities: no trailing newline, blank lines, tabs, CRLF, leading blanks, comments, extra
+    # columns, ids larger than 32 bits, a sign
+    odd = ('# a comment\n\n12 34\n  7\t8  \r\n\n5000000000 6 extra columns 9\n+3 -4\n   \n99 100')
+    p2 = str(tmp_path / 'odd.txt')
+    open(p2, 'w').write(odd)
+    c0, c1 = graph.read_edge_list_device(p2)
+    assert c0.tolist() == [12, 7, 5000000000, 3, 99] and c1.tolist() == [34, 8, 6, -4, 100]
+    # (3) a data line with one column is an error, not a silent zero
+    p3 = str(tmp_path / 'bad.txt')
+    open(p3, 'w').write('1 2\n3\n4 5\n')
+    with pytest.raises(ValueError):
+        graph.read_edge_list_device(p3)
+    # (4) the whole route: text -> device parse -> device compaction -> device build == host route
+    pu, pv = synth.make_pairs(3000, 400, eu, eb, 5000, k=5, seed=42)
+    ipu, ipv = synth.shared_ids(3000, pu, pv)
+    Gd = graph.BipartiteGraph.from_edge_list(path)                      # parse='device'
+    Gh = graph.BipartiteGraph.from_edge_list(path, parse='host')
+    assert np.array_equal(Gd.user_ids, Gh.user_ids) and np.array_equal(Gd.biz_ids, Gh.biz_ids)
+    a, b = Gd.score_id_pairs(ipu, ipv), Gh.score_id_pairs(ipu, ipv)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    # an id on both sides is refused on the device route as well
+    p4 = str(tmp_path / 'notbip.txt')
+    open(p4, 'w').write('1 2\n2 3\n')
+    with pytest.raises(ValueError):
+        graph.BipartiteGraph.from_edge_list(p4)
+    # an empty file has no edges
+    p5 = str(tmp_path / 'empty.txt')
+    open(p5, 'w').write('\n# nothing\n')
+    with pytest.raises(ValueError):
+        graph.BipartiteGraph.from_edge_list(p5)
