@@ -224,6 +224,7 @@ void read_tuning(blp_tuning* t) {
     if (const char* e = getenv("BLP_LIGHT_STREAM")) t->light_stream = atoi(e) != 0;
     if (const char* e = getenv("BLP_SLICE_GROWTH")) t->slice_growth = atof(e);
     if (getenv("BLP_NO_BANK_STRIPE")) t->bank_stripe = false;
+    if (const char* e = getenv("BLP_HOP3_GLOBAL")) t->hop3_global = atoi(e) != 0;
 }
 
 // 1/ln(d) in Q1.31 for d = 0..max_deg (0 for d <= 1), evaluated with the host libm.

@@ -2,11 +2,15 @@
 // businesses at BFS distance exactly 3, i.e. what make_examples obtains from
 // snap.GetNodesAtHop(G, u, 3, candidate_businesses, True) (dataset_maker.py:137-139):
 //
-//   hop2(u) = ( U_{b in N(u)} N(b) ) \ {u}          user bitmap in shared memory
+//   hop2(u) = ( U_{b in N(u)} N(b) ) \ {u}          user bitmap
 //   hop3(u) = ( U_{w in hop2(u)} N(w) ) \ N(u)      business bitmap in shared memory
 //
 // One CTA per user, pulled from an atomic counter.  The first call counts, the second writes the
-// ids in ascending order at caller-provided offsets.
+// ids in ascending order at caller-provided offsets.  The user bitmap lives in shared memory when
+// both bitmaps fit one CTA (C1-C4); for larger user universes (C5: 10 M users = 1.25 MB) every
+// CTA owns a slice of a global scratch bitmap instead, kept all-zero between users by walking the
+// same lists again (an undo pass touches only the words that were set, a clear would touch all).
+#include <algorithm>
 #include <climits>
 #include <cstdio>
 
@@ -34,13 +38,16 @@ struct Hop3Args {
     const long long* offsets;              // fill pass
     int* out_biz;
     int* work_counter;
+    unsigned* ubm_global;                  // null: user bitmap in shared memory; else [gridDim.x][uw]
 };
 
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_hop3(Hop3Args a) {
     extern __shared__ __align__(16) unsigned h3_smem[];
-    unsigned* ubm = h3_smem;               // users at distance 2
-    unsigned* bbm = h3_smem + a.uw;        // businesses at distance 3
+    // users at distance 2 / businesses at distance 3
+    unsigned* ubm = a.ubm_global ? a.ubm_global + (size_t)blockIdx.x * (size_t)a.uw : h3_smem;
+    unsigned* bbm = a.ubm_global ? h3_smem : h3_smem + a.uw;
+    const int n_clear = a.ubm_global ? a.bw : a.uw + a.bw;   // (the global slice is kept clean)
     __shared__ int s_item;
     __shared__ int s_scan[9];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -56,7 +63,7 @@ __global__ void __launch_bounds__(256) k_hop3(Hop3Args a) {
             if (!FILL && tid == 0) a.counts[it] = 0;
             continue;
         }
-        for (int i = tid; i < a.uw + a.bw; i += 256) h3_smem[i] = 0u;
+        for (int i = tid; i < n_clear; i += 256) h3_smem[i] = 0u;
         __syncthreads();
         const unsigned long long urow = a.u_row[u];
         const int* nu = h3_list(a.u_adj, urow);
@@ -71,24 +78,60 @@ __global__ void __launch_bounds__(256) k_hop3(Hop3Args a) {
             }
         }
         __syncthreads();
-        if (tid == 0) ubm[u >> 5] &= ~(1u << (u & 31));   // distance 0, not 2
+        if (tid == 0) atomicAnd(&ubm[u >> 5], ~(1u << (u & 31)));   // distance 0, not 2
         __syncthreads();
-        // hop 3: every thread walks words of the user bitmap; each set bit is a user w whose
-        // (short) business list is marked
-        for (int i = tid; i < a.uw; i += 256) {
-            unsigned m = ubm[i];
-            while (m) {
-                const int w = i * 32 + __ffs(m) - 1;
-                m &= m - 1;
-                const unsigned long long wrow = a.u_row[w];
-                const int* lst = h3_list(a.u_adj, wrow);
-                for (int j = 0; j < h3_deg(wrow); ++j) {
-                    const int b = lst[j];
-                    atomicOr(&bbm[b >> 5], 1u << (b & 31));
+        // hop 3: a warp takes 32 words of the user bitmap at a time; the users found in them are
+        // dealt to the lanes round-robin (a warp-wide prefix over the popcounts numbers them), so
+        // the lanes walk about equally many of the (short) business lists instead of one lane
+        // getting a dense word and its neighbours an empty one
+        for (int base = warp * 32; base < a.uw; base += 8 * 32) {
+            const int i = base + lane;
+            // (global slice: the bits were set by atomics in L2 -- read there, not from a stale L1 line)
+            unsigned m = i < a.uw ? (a.ubm_global ? __ldcg(ubm + i) : ubm[i]) : 0u;
+            const int c = __popc(m);
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(kAll, inc, d);
+                if (lane >= d) inc += t;
+            }
+            const int total = __shfl_sync(kAll, inc, 31);
+            if (total == 0) continue;
+            const int excl = inc - c;
+            for (int r0 = 0; r0 < total; r0 += 32) {     // uniform trip count: the shuffles need every lane
+                const bool active = r0 + lane < total;
+                const int r = active ? r0 + lane : total - 1;
+                // the r-th user of the 32 words sits in the word of lane L = #{lanes : inc <= r}
+                int L = 0;
+#pragma unroll
+                for (int sft = 16; sft >= 1; sft >>= 1) {
+                    const int t = __shfl_sync(kAll, inc, L + sft - 1);
+                    if (t <= r) L += sft;
+                }
+                unsigned mm = __shfl_sync(kAll, m, L);
+                const int skip = r - __shfl_sync(kAll, excl, L);
+                if (active) {
+                    for (int q = 0; q < skip; ++q) mm &= mm - 1;
+                    const int w = (base + L) * 32 + __ffs(mm) - 1;
+                    const unsigned long long wrow = a.u_row[w];
+                    const int* lst = h3_list(a.u_adj, wrow);
+                    for (int j = 0; j < h3_deg(wrow); ++j) {
+                        const int b = lst[j];
+                        atomicOr(&bbm[b >> 5], 1u << (b & 31));
+                    }
                 }
             }
         }
         __syncthreads();
+        if (a.ubm_global) {
+            // undo: the same lists once more, zeroing the words they set (every set bit of a touched
+            // word belongs to this user's hop-2 set), so the slice is all-zero for the next user
+            for (int k = warp; k < du; k += 8) {
+                const unsigned long long brow = a.b_row[nu[k]];
+                const int* lst = h3_list(a.b_adj, brow);
+                for (int j = lane; j < h3_deg(brow); j += 32) ubm[lst[j] >> 5] = 0u;
+            }
+        }
         for (int k = tid; k < du; k += 256) {             // distance 1, not 3
             const int b = nu[k];
             atomicAnd(&bbm[b >> 5], ~(1u << (b & 31)));
@@ -137,9 +180,13 @@ int launch_hop3(blp_graph* g, Hop3Args a, bool fill, cudaStream_t st) {
     a.n_biz = g->n_biz;
     a.uw = (g->n_users + 31) / 32;
     a.bw = (g->n_biz + 31) / 32;
-    const size_t smem = sizeof(unsigned) * ((size_t)a.uw + a.bw);
+    // both bitmaps in shared memory when they fit; else only the business bitmap, and the user
+    // bitmap of every CTA in global scratch (BLP_HOP3_GLOBAL=1 forces that, for tests)
+    size_t smem = sizeof(unsigned) * ((size_t)a.uw + a.bw);
+    const bool global_users = g->tune.hop3_global || smem + 1024 > (size_t)g->max_smem_optin;
+    if (global_users) smem = sizeof(unsigned) * (size_t)a.bw;
     if (smem + 1024 > (size_t)g->max_smem_optin) {
-        set_error("blp_hop3: user + business bitmaps exceed one CTA's shared memory");
+        set_error("blp_hop3: the business bitmap alone exceeds one CTA's shared memory");
         return BLP_ERR_UNSUPPORTED;
     }
     int* counter = nullptr;
@@ -150,12 +197,21 @@ int launch_hop3(blp_graph* g, Hop3Args a, bool fill, cudaStream_t st) {
     if (fill) {
         BLP_CUDA_TRY(cudaFuncSetAttribute(k_hop3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         BLP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hop3<true>, 256, smem));
-        k_hop3<true><<<std::max(1, per_sm) * g->sm_count, 256, smem, st>>>(a);
     } else {
         BLP_CUDA_TRY(cudaFuncSetAttribute(k_hop3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         BLP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hop3<false>, 256, smem));
-        k_hop3<false><<<std::max(1, per_sm) * g->sm_count, 256, smem, st>>>(a);
     }
+    int grid = std::max(1, per_sm) * g->sm_count;
+    if (global_users) {
+        // at most 1 GiB of scratch bitmaps: fewer CTAs rather than more memory
+        const size_t per_cta = sizeof(unsigned) * (size_t)a.uw;
+        grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)grid, ((size_t)1 << 30) / std::max<size_t>(per_cta, 1)));
+        BLP_CUDA_TRY(pool_alloc(g, (void**)&a.ubm_global, per_cta * (size_t)grid, st));
+        BLP_CUDA_TRY(cudaMemsetAsync(a.ubm_global, 0, per_cta * (size_t)grid, st));
+    }
+    if (fill) k_hop3<true><<<grid, 256, smem, st>>>(a);
+    else k_hop3<false><<<grid, 256, smem, st>>>(a);
+    if (a.ubm_global) cudaFreeAsync(a.ubm_global, st);
     BLP_CUDA_TRY(cudaGetLastError());
     cudaFreeAsync(counter, st);
     return BLP_OK;

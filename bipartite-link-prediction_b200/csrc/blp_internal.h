@@ -31,6 +31,7 @@ struct blp_tuning {
     bool light_stream = true;  // BLP_LIGHT_STREAM=0: keep k_score_light on the caller's stream
     double slice_growth = 0.0; // BLP_SLICE_GROWTH: user-side slice plan of blp_score_pairs_host
     bool bank_stripe = true;   // BLP_NO_BANK_STRIPE: leave long rows in ascending order
+    bool hop3_global = false;  // BLP_HOP3_GLOBAL=1: hop-3 user bitmap in global scratch even when it fits shared memory
 };
 
 struct blp_graph {

@@ -10,9 +10,14 @@ from test_gpu_parity import mods  # noqa: F401
 pytestmark = pytest.mark.gpu
 
 
-def test_hop3_sets_match_bfs(mods):
+@pytest.mark.parametrize('global_bitmap', [False, True])
+def test_hop3_sets_match_bfs(mods, monkeypatch, global_bitmap):
+    """global_bitmap: the hop-2 user bitmap of every CTA in global scratch (what universes beyond
+    one CTA's shared memory use, C5) instead of shared memory -- same sets."""
     from oracle import similarity_oracle as oa
     graph, synth = mods
+    if global_bitmap:
+        monkeypatch.setenv('BLP_HOP3_GLOBAL', '1')      # read when the handle is created
     for seed, n_users, n_biz, n_rev in ((0, 400, 90, 1500), (1, 3000, 60, 5000), (2, 60, 700, 900)):
         eu, eb = synth.make_graph(n_users, n_biz, n_rev, seed=seed, shift_u=2.0, shift_b=2.0)
         G = graph.BipartiteGraph(n_users, n_biz, eu, eb)
@@ -68,3 +73,22 @@ def test_make_examples_structure_and_timing(mods):
     total = sum(len(v) for v in ex.values())
     all_c = sum(len(v) for v in cand.values()) / 200 * users.size
     assert 0.02 * all_c < total < 0.09 * all_c                  # ~5 % of the negatives survive
+
+
+def test_hop3_universe_larger_than_shared_memory(mods):
+    """2.5M users: the hop-2 user bitmap (312 KB) cannot live in one CTA's shared memory -- the
+    kernel keeps it in global scratch (round 1 returned BLP_ERR_UNSUPPORTED here)."""
+    from oracle import similarity_oracle as oa
+    graph, synth = mods
+    n_users, n_biz = 2_500_000, 3000
+    eu, eb = synth.make_graph(n_users, n_biz, 400_000, seed=5, shift_u=50.0, shift_b=5.0)
+    G = graph.BipartiteGraph(n_users, n_biz, eu, eb)
+    ids_eu, ids_eb = synth.shared_ids(n_users, eu, eb)
+    O = oa.MiniSnapGraph.from_edges(zip(ids_eu.tolist(), ids_eb.tolist()))
+    rng = np.random.default_rng(2)
+    users = np.concatenate([rng.choice(np.unique(eu), size=60, replace=False), [-1, n_users + 5]]).astype(np.int32)
+    off, biz = G.hop3_candidates(users)
+    off, biz = off.cpu().numpy(), biz.cpu().numpy()
+    for i, u in enumerate(users.tolist()):
+        want = sorted(b - n_users for b in oa.hop3_candidates(O, u)) if 0 <= u < n_users else []
+        assert biz[off[i]:off[i + 1]].tolist() == want, u
