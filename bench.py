@@ -474,6 +474,7 @@ def main():
     ap.add_argument('--cpu-biz-groups', type=int, default=None)
     ap.add_argument('--no-other-configs', action='store_true',
                     help='skip the short C3 / C4 lines that follow the headline measurement')
+    ap.add_argument('--derive', default=None, help="N>1: comma list of columns rank 0 derives (default pa)")
     ap.add_argument('--quick', action='store_true',
                     help='headline measurement and checks only: no comparison arms, no e2e, no other configs')
     a = ap.parse_args()
@@ -615,7 +616,8 @@ def main():
         pu, pv = pu_all[lo:hi], pv_all[lo:hi]              # this rank's slice from here on
         if rank != 0:
             del all_u, all_b
-        window = dmod.ResultWindow(G, n_total, columns=dmod.REFERENCE_COLUMNS, dst=0)
+        window = dmod.ResultWindow(G, n_total, columns=dmod.REFERENCE_COLUMNS, dst=0,
+                                   derived=tuple(a.derive.split(',')) if a.derive else None)
         if rank == 0:
             window.attach_pairs(all_u, all_b, (lo, hi))
     else:
@@ -632,14 +634,14 @@ def main():
         # stream, so that the per-kernel event times below are those of the kernels alone
         nonlocal outs, mid_event
         if window is not None and not local:
-            # peers store cn / union / adamic of both sides (32 B per pair) into rank 0's window;
-            # rank 0 derives jaccard and pa for their rows once every rank's kernels are done
+            # peers store their rows into rank 0's window; rank 0 derives what the window's
+            # `derived` names (default: pa, under its own scoring; nothing after the rows have landed)
             dmod.score_into_window(G, d_u, d_b, window, lo)
             if mid_event is not None:
                 mid_event.record()
             dmod.rows_landed(G)
             if rank == 0:
-                window.derive()        # jaccard of the peers' rows (their pa was derived under the scoring)
+                window.derive()        # whatever is left to derive for the peers' rows (default: nothing)
         else:
             outs = G.score_pairs(d_u, d_b, out=outs, concurrent=concurrent)
 
@@ -764,9 +766,9 @@ def main():
                  'slice_pairs': counts,
                  'fused_window': {'ms_per_step': ms_per_step, 'value': value, 'unit': UNIT,
                                   'wall_ms_per_step_with_barriers': wall_ms_per_step,
-                                  'what': 'every rank\'s kernels store cn / union / adamic of its rows into rank 0\'s '
-                                          'peer-mapped window, rank 0 derives jaccard and pa '
-                                          '(this is the line\'s `value`)'},
+                                  'what': 'every rank\'s kernels store its rows into rank 0\'s peer-mapped window '
+                                          '(the business side by copy engine under the user-side kernels); '
+                                          'rank 0 derives %s (this is the line\'s `value`)' % ', '.join(window.derived)},
                  'scoring_only': {'ms_per_step': l_ms, 'value': n_total / (l_ms * 1e-3), 'unit': UNIT,
                                   'what': 'same slices scored into local memory, nothing gathered'},
                  'nccl_gather': {'gather_ms': g_ms, 'ms_per_step': l_ms + g_ms,

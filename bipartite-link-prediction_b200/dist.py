@@ -13,11 +13,14 @@ How the slices meet again on rank `dst`:
     ``blp_score_pairs`` as its output pointers, so the scoring kernels' own epilogue stores carry
     every row over NVLink / NVSwitch while the rest of the slice is still being scored: compute
     and "gather" are one kernel, no SM runs a copy, no second pass over the results.
-    Only the columns that carry information cross the link: cn, union and adamic of both sides,
-    32 of the 56 bytes per pair.  jaccard (= cn / union, the kernels' own IEEE division) and pa
-    (= deg(u) * deg(v), from the replicated degree arrays) are exact functions of those and are
-    derived on `dst` by ``blp_derive_pairs`` once the peers' rows have landed -- bit-identical to
-    what the scoring kernels write themselves.
+    pa (= deg(u) * deg(v)) is a function of the pair ids and the replicated degree arrays alone:
+    it never crosses the link, `dst` derives it for the peers' rows (``blp_derive_pairs``) on a
+    side stream under its own scoring kernels, so nothing is left to do once the peers' rows have
+    landed (40 of the 48 reference bytes per pair on the wire).  jaccard (= cn / union, the kernels'
+    own IEEE division) can be derived on `dst` as well (``derived=``: 32 or 36 bytes on the wire,
+    a pass over the peers' rows after they have landed); measured at 8 GPUs all three variants
+    work, the default is the fastest (profiles/r02_notes.md).  Derived columns are bit-identical
+    to what the scoring kernels write themselves.
   * ``gather_results``  (the baseline it is measured against, and what the gloo CPU test uses):
     score into local memory, then move every column slice with one grouped batch of
     point-to-point send / recv straight into place (NCCL over NVLink on the box).
@@ -36,10 +39,11 @@ import numpy as np
 REFERENCE_COLUMNS = ('u_cn', 'u_jaccard', 'u_adamic', 'b_cn', 'b_jaccard', 'b_adamic', 'pa')
 # ... plus the two union sizes (not reference outputs; tests and the roofline use them): 56 B
 ALL_COLUMNS = REFERENCE_COLUMNS + ('u_union', 'b_union')
-# what a peer's kernels store into the window (32 B per pair) ...
+# the least a peer's kernels must store into the window (32 B per pair) ...
 WIRE_COLUMNS = ('u_cn', 'u_union', 'u_adamic', 'b_cn', 'b_union', 'b_adamic')
-# ... and what `dst` derives from them and the replicated graph
+# ... what `dst` CAN derive from them and the replicated graph, and what it derives by default
 DERIVED_COLUMNS = ('u_jaccard', 'b_jaccard', 'pa')
+DEFAULT_DERIVED = ('pa',)
 _ITEMSIZE = {'cn': 4, 'union': 4, 'jaccard': 8, 'adamic': 8, 'pa': 8}
 
 
@@ -106,12 +110,13 @@ class ResultWindow(object):
 
     Collective: every rank of `group` constructs it (the IPC handle is broadcast from `dst`).
     ``columns`` selects what `dst` ends up with; a column that is left out is not computed.
-    With ``compact`` (default) the peers store only the WIRE_COLUMNS and `dst` derives
-    DERIVED_COLUMNS afterwards (``derive``); the union columns this needs are kept internally even
-    when they were not asked for.
+    With ``compact`` (default) the peers do not store the columns in ``derived`` (default
+    DEFAULT_DERIVED = pa; any subset of DERIVED_COLUMNS): `dst` computes them (``derive``); the
+    union columns a derived jaccard needs are kept internally even when they were not asked for.
     """
 
-    def __init__(self, graph, n_total, columns=REFERENCE_COLUMNS, dst=0, group=None, compact=True):
+    def __init__(self, graph, n_total, columns=REFERENCE_COLUMNS, dst=0, group=None, compact=True,
+                 derived=None):
         import torch.distributed as dist
         from . import _lib
         self._lib = _lib.load()
@@ -122,11 +127,18 @@ class ResultWindow(object):
         if bad:
             raise ValueError('unknown result columns %r' % (bad,))
         self.compact = bool(compact)
+        # which columns `dst` derives instead of receiving.  Default ('pa',): 40 B per pair on the
+        # wire and nothing left to do after the peers' rows have landed, pa being a function of
+        # the pair ids alone; DERIVED_COLUMNS: 32 B on the wire, jaccard derived afterwards
+        self.derived = tuple(DEFAULT_DERIVED if derived is None else derived) if self.compact else ()
+        bad = [c for c in self.derived if c not in DERIVED_COLUMNS]
+        if bad:
+            raise ValueError('cannot derive %r on the destination' % (bad,))
         self.graph = graph
         alloc = list(self.columns)
         if self.compact:                         # jaccard is derived from (cn, union) on `dst`
             for side in 'ub':
-                if side + '_jaccard' in alloc:
+                if side + '_jaccard' in alloc and side + '_jaccard' in self.derived:
                     alloc += [c for c in (side + '_cn', side + '_union') if c not in alloc]
         self._alloc_columns = tuple(alloc)
         self.dst = dst
@@ -174,7 +186,7 @@ class ResultWindow(object):
         second pass), the wire columns only on a peer of a compact window."""
         if self._owner or not self.compact:
             return self._alloc_columns
-        return tuple(c for c in self._alloc_columns if c not in DERIVED_COLUMNS)
+        return tuple(c for c in self._alloc_columns if c not in self.derived)
 
     def pointers(self, lo, columns=None):
         """Device addresses of row `lo` of the columns, valid on THIS rank's device."""
@@ -183,8 +195,7 @@ class ResultWindow(object):
 
     def bytes_per_pair(self):
         """Bytes per pair a peer sends over the link."""
-        cols = self._alloc_columns if not self.compact else \
-            tuple(c for c in self._alloc_columns if c not in DERIVED_COLUMNS)
+        cols = tuple(c for c in self._alloc_columns if c not in self.derived)
         return sum(_ITEMSIZE[_kind(c)] for c in cols)
 
     def attach_pairs(self, d_all_u, d_all_b, own):
@@ -214,7 +225,7 @@ class ResultWindow(object):
             d_all_u, d_all_b, own = self._pairs
             if which is None:
                 skip = self._early
-        want = [c for c in self._alloc_columns if c in DERIVED_COLUMNS and c not in skip and
+        want = [c for c in self._alloc_columns if c in self.derived and c not in skip and
                 (which is None or c in which)]
         if not want:
             return

@@ -42,6 +42,12 @@ def main():
 
         # (a) fused: every rank's kernels write rank 0's window
         cols, window = d.score_sharded(G, pu, pv, cost=cost, columns=d.ALL_COLUMNS)
+        # (a') the same with the 32-byte wire format: rank 0 derives jaccard of both sides and pa
+        w32 = d.ResultWindow(G, len(pu), columns=d.ALL_COLUMNS, derived=d.DERIVED_COLUMNS)
+        cols32, _ = d.score_sharded(G, pu, pv, cost=cost, window=w32)
+        same32 = True
+        if rank == 0:
+            same32 = all(torch.equal(cols32[k], cols[k]) for k in cols) and w32.bytes_per_pair() == 32
         # (b) baseline: local scoring + grouped NCCL send/recv
         t_u = torch.from_numpy(pu[lo:hi]).to(dev)
         t_b = torch.from_numpy(pv[lo:hi]).to(dev)
@@ -69,9 +75,11 @@ def main():
                    'window_vs_unsharded': 'ok' if not bad_whole else 'mismatch in %s' % bad_whole,
                    'nccl_gather_vs_window': 'ok' if not bad_nccl else 'mismatch in %s' % bad_nccl,
                    'rows_checked_per_rank': counts,
+                   'compact32_vs_window': 'ok' if same32 else 'mismatch',
                    'bytes_per_pair_over_nvlink': window.bytes_per_pair()}
         dist.barrier()
         window.close()
+        w32.close()
         if rank == 0:
             with open(report_path, 'w') as fh:
                 json.dump(rep, fh)

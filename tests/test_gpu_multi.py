@@ -5,8 +5,8 @@ box -- the driver's scaling run and `gpurun --gpus N` provide more).  Every rank
 user-aligned, work-balanced slice of ONE pair list (`dist.shard_bounds`); the rows of ALL ranks are
 compared on rank 0 with the C oracle and with the unsharded single-GPU call, for both ways of
 bringing them together:
-  * `dist.score_sharded`   -- the scoring kernels store cn / union / adamic straight into rank 0's
-                              peer-mapped window; rank 0 derives jaccard and pa (blp_derive_pairs)
+  * `dist.score_sharded`   -- the scoring kernels store their rows straight into rank 0's peer-mapped
+                              window; rank 0 derives pa (default) or jaccard and pa (blp_derive_pairs)
   * `dist.gather_results`  -- local scoring, then one grouped batch of NCCL send / recv
 """
 import json
@@ -49,4 +49,4 @@ def test_sharded_scoring_all_ranks_match_oracle(built_lib, tmp_path):
     assert rep['window_vs_unsharded'] == 'ok', rep
     assert rep['nccl_gather_vs_window'] == 'ok', rep
     assert rep['rows_checked_per_rank'] and min(rep['rows_checked_per_rank']) > 0
-    assert rep['bytes_per_pair_over_nvlink'] == 32      # cn, union, adamic of both sides; the rest is derived
+    assert rep['bytes_per_pair_over_nvlink'] == 48 and rep['compact32_vs_window'] == 'ok'
