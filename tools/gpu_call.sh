@@ -1,11 +1,11 @@
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/c23_pytest.log 2>&1; echo "pytest rc $?"; tail -4 gpurun_out/c23_pytest.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29553 bench.py --gpus 2 --steps 10 --warmup 3 --no-other-configs > gpurun_out/c23_bench_n2.json 2> gpurun_out/c23_bench_n2.err; echo "bench rc $?"; tail -c 400 gpurun_out/c23_bench_n2.err
+timeout 900 python bench.py > gpurun_out/c24_bench_n1.json 2> gpurun_out/c24_bench_n1.err; echo "bench rc $?"; tail -c 300 gpurun_out/c24_bench_n1.err
 python - <<PY
 import json
-try:
-    d=json.loads(open('gpurun_out/c23_bench_n2.json').read().strip().splitlines()[-1])
-    m=d['multi_gpu']; print('N=2 value', d['value'], 'ms', d['ms_per_step'], m['bytes_per_pair_over_nvlink']); print(m['fused_window']['ms_per_step'], m['scoring_only']['ms_per_step'], m['all_rows_match_unsharded_call'], m['nccl_gather_rows_match'], m['oracle_check']['ok']); print(m['fused_window']['what'])
-except Exception as e: print('no json', e)
+d=json.loads(open('gpurun_out/c24_bench_n1.json').read().strip().splitlines()[-1])
+print('value', d['value'], d['ms_per_step'], d['clocks'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'launches', d['gpu_launches'])
+print('roof', d['roofline']['frac'], d['roofline']['kernel_ms'], d['roofline']['traffic'], d['roofline'].get('intersection_phase',{}).get('frac'))
+print('parity', d['parity_full_workload']['ok']); print('cpu', d['cpu_baseline']['value'])
+for o in d['other_configs']: print(o['config'], o.get('value'), o.get('roofline',{}).get('frac'), o.get('parity_sample',{}).get('ok'), o.get('error'))
 PY
