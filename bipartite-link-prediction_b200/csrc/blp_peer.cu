@@ -15,8 +15,9 @@
 
 static_assert(sizeof(cudaIpcMemHandle_t) == BLP_IPC_HANDLE_BYTES, "handle size is part of the ABI");
 
-// The columns that are exact functions of the others and of the (replicated) graph are not sent
-// over the link at all: the destination rank derives them where they are needed.
+// The columns that are exact functions of the others and of the (replicated) graph need not be
+// sent over the link: the destination rank can derive them where they are needed (pa always is;
+// jaccard is an option of dist.ResultWindow).
 //   jaccard = (double)cn / (double)union   (similarity.py:108-111; IEEE division, the very
 //             expression the scoring kernels evaluate) -- 0.0 for a pair that is not in the graph
 //   pa      = deg(u) * deg(v)              ("Link prediction.R":400-415), 0 when not in the graph

@@ -242,8 +242,10 @@ int blp_peer_push(int device, void* dst, const void* src, int64_t bytes, void* s
  * are needed instead of being moved: u_jaccard / b_jaccard from (cn, union) with the scoring
  * kernels' own expression (similarity.py:108-111; 0.0 where union is 0, i.e. the pair is not in the
  * graph) and pa = deg(u) * deg(v) from the pair ids ("Link prediction.R":400-415).  The multi-GPU
- * path sends only cn / union / adamic of both sides through the peer window (32 of the 56 bytes per
- * pair) and calls this on the destination rank.  DEVICE arrays of n elements; any output may be NULL.
+ * path does not send pa through the peer window at all (it is a function of the pair ids alone)
+ * and can leave jaccard out as well (32 instead of 40 of the 48 reference bytes per pair on the
+ * wire); the destination rank calls this for the peers' rows.  DEVICE arrays of n elements; any
+ * output may be NULL.
  */
 int blp_derive_pairs(blp_graph* g, const int32_t* pair_u, const int32_t* pair_b, int64_t n,
                      const int32_t* u_cn, const int32_t* u_union, const int32_t* b_cn,
