@@ -1049,7 +1049,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
     // a dozen allocator calls before the first kernel): carved by a bump pointer, 256-byte aligned
     const size_t n_sz = (size_t)n, k_sz = (size_t)n_keys, i_sz = std::max(n_sz, k_sz);
     const size_t arena_bytes = 4 * n_sz + 20 * i_sz + 8 * k_sz + 12 * n_sz + 24 * n_sz +
-                               (ranged ? 12 * n_sz : 0) + 64 * 256;
+                               (ranged ? 12 * n_sz : 0) + 8 * (k_sz / kScanTile + 1) + 64 * 256;
     unsigned char* arena = nullptr;
     size_t arena_used = 0;
     {
@@ -1134,12 +1134,19 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         BLP_TRY_SCRATCH(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
         k_group_count<<<gblocks, 256, 0, st>>>(mode, keys, n, cnt);
         BLP_TRY_SCRATCH(cudaGetLastError());
-        k_group_scan<<<1, 1024, 0, st>>>(mode, cnt, n_keys, grp_off, item_key, item_start,
-                                         item_end, scalars);
+        const int n_tiles = (n_keys + kScanTile - 1) / kScanTile;
+        unsigned* tile_sum = nullptr;
+        int* tile_items = nullptr;
+        BLP_TRY_SCRATCH(alloc((void**)&tile_sum, sizeof(unsigned) * (size_t)n_tiles));
+        BLP_TRY_SCRATCH(alloc((void**)&tile_items, sizeof(int) * (size_t)n_tiles));
+        k_group_tile_sums<<<n_tiles, 1024, 0, st>>>(mode, cnt, n_keys, tile_sum, tile_items);
+        k_group_tile_scan<<<1, 1024, 0, st>>>(mode, tile_sum, tile_items, n_tiles, scalars);
+        k_group_tile_apply<<<n_tiles, 1024, 0, st>>>(mode, cnt, n_keys, tile_sum, tile_items, grp_off,
+                                                      item_key, item_start, item_end);
         BLP_TRY_SCRATCH(cudaGetLastError());
         k_group_scatter<<<gblocks, 256, 0, st>>>(mode, keys, gy, n, grp_off, pg, inv);
         BLP_TRY_SCRATCH(cudaGetLastError());
-        launches += 3;
+        launches += 5;
         a.pg = pg;
     }
     a.mode = mode;
