@@ -316,3 +316,26 @@ def test_large_configs_sampled_parity(mods, name, n_pairs, n_check):
     idx = np.arange(0, pu.size, pu.size // n_check)[:n_check]
     want = c_oracle.score_pair_arrays(cfg['n_users'], cfg['n_biz'], eu, eb, pu[idx], pv[idx])
     check_against({k: v[idx] for k, v in got.items()}, want, idx.size)
+
+
+@pytest.mark.timeout(900)
+def test_c5_shape_at_half_scale_sampled_parity(mods):
+    """BASELINE.json configs[4] (10M users x 1M businesses, 100M reviews) at half the node counts
+    and a quarter of the reviews -- still the regime the config is about: the user-side universe
+    (5M bits = 625 KB) is far beyond one CTA's shared memory, so every group takes several
+    id-range passes over range-partitioned rows.  A strided sample against the C oracle.  (The
+    full-scale graph takes minutes to generate on the host; its sharded run with the same check is
+    recorded in profiles/r02_bench_c5_n2.json: `bench.py --config C5 --gpus 2 --quick`.)"""
+    from oracle import c_oracle
+    graph, synth = mods
+    lib = pkg('_lib')
+    cfg = dict(synth.CONFIGS['C5'])
+    cfg.update(n_users=5_000_000, n_biz=500_000, n_reviews=25_000_000, n_pairs=2_000_000)
+    eu, eb = synth.make_graph(seed=0, **cfg)
+    pu, pv = synth.make_pairs(edge_u=eu, edge_b=eb, seed=1, **cfg)
+    G = graph.BipartiteGraph(cfg['n_users'], cfg['n_biz'], eu, eb)
+    got = G.score_pairs_host(pu, pv)
+    assert G.score_stats(lib.SIDE_USER)['range_passes'] >= 3
+    idx = np.arange(0, pu.size, pu.size // 6000)[:6000]
+    want = c_oracle.score_pair_arrays_parallel(cfg['n_users'], cfg['n_biz'], eu, eb, pu[idx], pv[idx], threads=4)
+    check_against({k: v[idx] for k, v in got.items()}, want, idx.size)
