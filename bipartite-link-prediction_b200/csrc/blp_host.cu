@@ -102,10 +102,11 @@ extern "C" int blp_score_pairs_host(blp_graph* g, const int32_t* pair_u, const i
     if (rc != BLP_OK) return rc;
     blp_host_state* h = g->host;
 
-    // slice plan (defaults measured on C2, tools/e2e_time.py)
+    // slice plan (defaults measured on C2 with the 48-byte result set, tools/e2e_time.py: 4/1/2 10.4 ms,
+    // 5/1/2 10.5, 6/1/2 11.0, 8/1/2 11.9, 3/1/2 11.0, 4/1/1 10.9 -- every slice costs a grouping pass and a tail)
     const int64_t min_slice = 65536;
     const int max_slices = (int)std::max<int64_t>(1, n / min_slice);
-    const int uc = std::max(1, std::min(user_slices > 0 ? user_slices : 5, max_slices));
+    const int uc = std::max(1, std::min(user_slices > 0 ? user_slices : 4, max_slices));
     const int bc = std::max(1, std::min(biz_slices > 0 ? biz_slices : 2, max_slices));
     const int lead = std::max(0, std::min(lead_slices >= 0 ? lead_slices : 1, uc - 1));
     const double slice_growth = g->tune.slice_growth;   // (BLP_SLICE_GROWTH, read at handle creation)

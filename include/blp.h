@@ -168,7 +168,7 @@ int blp_score_pairs(blp_graph* g, int side,
  * is copied back inside the call, which returns when the results are in host memory.  The copies
  * overlap the kernels: the user side runs in `user_slices` slices, the first `lead_slices` of them
  * before the rest of the ids are up, the business side in `biz_slices` slices between them
- * (<= 0 / < 0 / <= 0 select the defaults 5 / 1 / 2).  Outputs as in blp_score_pairs; a NULL column is
+ * (<= 0 / < 0 / <= 0 select the defaults 4 / 1 / 2).  Outputs as in blp_score_pairs; a NULL column is
  * not copied back (the link is the bottleneck of this call: 56 bytes per pair for all nine).
  * Not re-entrant on one handle (it owns the handle's staging buffers and streams).
  */

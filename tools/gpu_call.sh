@@ -1,3 +1,3 @@
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 800 python -m pytest tests/test_gpu_more.py -x -q -k "c5_shape" 2>&1 | tail -3
+timeout 300 python tools/e2e_time.py 2>&1 | tail -14
