@@ -1087,18 +1087,23 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         BLP_TRY_SCRATCH(alloc((void**)&a.acc_aa, sizeof(unsigned long long) * (size_t)n));
     }
 
-    BLP_TRY_SCRATCH(cudaEventRecord(g->ev[side][0], st));
-    const int gblocks = (int)std::min<long long>((n + 255) / 256, (long long)g->sm_count * 16);
-    int launches = 1;
-    k_group_keys<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, g_deg, m_deg, keys);
-    BLP_TRY_SCRATCH(cudaGetLastError());
-
     // Pairs that already arrive grouped (the reference's examples.json stores them per user) need
     // no sort: the runs of equal keys are the work items when they average >= 4 pairs.  The
     // decision is taken on the device (k_decide_mode); the kernels of the mode not chosen exit at
     // once, so the call never waits for the host.
     int force = g->tune.grouping;   // (BLP_GROUPING=runs|sort, read at handle creation)
     if (!us && force < 0) force = MODE_SORT;   // a per-user list is never grouped by business
+    unsigned* cnt = nullptr;
+    if (force == MODE_SORT) {   // the mode is certain: the keys pass counts the group sizes as well
+        BLP_TRY_SCRATCH(alloc((void**)&cnt, sizeof(unsigned) * (size_t)n_keys));
+        BLP_TRY_SCRATCH(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
+    }
+    BLP_TRY_SCRATCH(cudaEventRecord(g->ev[side][0], st));
+    const int gblocks = (int)std::min<long long>((n + 255) / 256, (long long)g->sm_count * 16);
+    int launches = 1;
+    k_group_keys<<<gblocks, 256, 0, st>>>(gx, gy, n, a.n_side, n_mid, g_deg, m_deg, keys, cnt);
+    BLP_TRY_SCRATCH(cudaGetLastError());
+
     int* mode = scalars + 3;
     if (force < 0) {
         k_count_runs<<<gblocks, 256, 0, st>>>(keys, n, (unsigned*)(scalars + 2));
@@ -1121,19 +1126,23 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         ++launches;
     }
     if (force != MODE_RUNS) {
-        unsigned *cnt = nullptr, *grp_off = nullptr;
+        unsigned* grp_off = nullptr;
         int2* pg = nullptr;
+        const bool counted = cnt != nullptr;
         BLP_TRY_SCRATCH(alloc((void**)&inv, sizeof(int) * (size_t)n));
         // grouped-order result records + gather pass: only when the sort mode is certain (the
         // business side); a list whose mode is decided on the device writes its outputs directly
         if (force == MODE_SORT)
             BLP_TRY_SCRATCH(alloc((void**)&a.rec, sizeof(unsigned long long) * 3 * (size_t)n));
-        BLP_TRY_SCRATCH(alloc((void**)&cnt, sizeof(unsigned) * (size_t)n_keys));
+        if (!counted) BLP_TRY_SCRATCH(alloc((void**)&cnt, sizeof(unsigned) * (size_t)n_keys));
         BLP_TRY_SCRATCH(alloc((void**)&grp_off, sizeof(unsigned) * (size_t)n_keys));
         BLP_TRY_SCRATCH(alloc((void**)&pg, sizeof(int2) * (size_t)n));
-        BLP_TRY_SCRATCH(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
-        k_group_count<<<gblocks, 256, 0, st>>>(mode, keys, n, cnt);
-        BLP_TRY_SCRATCH(cudaGetLastError());
+        if (!counted) {
+            BLP_TRY_SCRATCH(cudaMemsetAsync(cnt, 0, sizeof(unsigned) * (size_t)n_keys, st));
+            k_group_count<<<gblocks, 256, 0, st>>>(mode, keys, n, cnt);
+            BLP_TRY_SCRATCH(cudaGetLastError());
+            ++launches;
+        }
         const int n_tiles = (n_keys + kScanTile - 1) / kScanTile;
         unsigned* tile_sum = nullptr;
         int* tile_items = nullptr;
@@ -1146,7 +1155,7 @@ extern "C" int blp_score_pairs(blp_graph* g, int side, const int32_t* pair_u, co
         BLP_TRY_SCRATCH(cudaGetLastError());
         k_group_scatter<<<gblocks, 256, 0, st>>>(mode, keys, gy, n, grp_off, pg, inv);
         BLP_TRY_SCRATCH(cudaGetLastError());
-        launches += 5;
+        launches += 4;
         a.pg = pg;
     }
     a.mode = mode;

@@ -24,12 +24,19 @@ __device__ __forceinline__ int group_key(int x, int y, int n_side, int n_mid,
     return ok ? x : n_side;   // similarity.py:52,59-60: any id not in the graph -> literal 0
 }
 
+// `cnt` (may be null): the group sizes are counted in the same pass when the sort mode is certain
+// (the business side), which saves the counting sort's first pass over the keys
 __global__ void k_group_keys(const int* __restrict__ gx, const int* __restrict__ gy, long long n,
                              int n_side, int n_mid, const int* __restrict__ g_deg,
-                             const int* __restrict__ m_deg, int* __restrict__ keys) {
+                             const int* __restrict__ m_deg, int* __restrict__ keys,
+                             unsigned* __restrict__ cnt) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) keys[i] = group_key(gx[i], gy[i], n_side, n_mid, g_deg, m_deg);
+    for (; i < n; i += stride) {
+        const int key = group_key(gx[i], gy[i], n_side, n_mid, g_deg, m_deg);
+        keys[i] = key;
+        if (cnt) atomicAdd(&cnt[key], 1u);
+    }
 }
 
 constexpr int kRunCut = 4096;   // runs are cut at multiples of this, bounding the serial scan below
@@ -286,13 +293,32 @@ __global__ void k_unpermute(const int* __restrict__ mode, const unsigned long lo
     if (*mode != MODE_SORT) return;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        const unsigned long long* r = rec + 3ll * ld_once(inv + i);
-        const unsigned long long c = ld_once(r);
-        if (cn) st_stream(cn + i, (int)(unsigned)c);
-        if (uni) st_stream(uni + i, (int)(unsigned)(c >> 32));
-        if (jac) st_stream(jac + i, __longlong_as_double((long long)ld_once(r + 1)));
-        if (aa) st_stream(aa + i, __longlong_as_double((long long)ld_once(r + 2)));
+    // two rows per trip: the two dependent chains (inverse index -> 24-byte record) overlap
+    for (; i < n; i += 2 * stride) {
+        const long long i1 = i + stride;
+        const bool two = i1 < n;
+        const unsigned long long* r0 = rec + 3ll * ld_once(inv + i);
+        const unsigned long long* r1 = rec + 3ll * ld_once(inv + (two ? i1 : i));
+        const unsigned long long c0 = ld_once(r0), c1 = ld_once(r1);
+        unsigned long long j0 = 0, j1 = 0, a0 = 0, a1 = 0;
+        if (jac) {
+            j0 = ld_once(r0 + 1);
+            j1 = ld_once(r1 + 1);
+        }
+        if (aa) {
+            a0 = ld_once(r0 + 2);
+            a1 = ld_once(r1 + 2);
+        }
+        if (cn) st_stream(cn + i, (int)(unsigned)c0);
+        if (uni) st_stream(uni + i, (int)(unsigned)(c0 >> 32));
+        if (jac) st_stream(jac + i, __longlong_as_double((long long)j0));
+        if (aa) st_stream(aa + i, __longlong_as_double((long long)a0));
+        if (two) {
+            if (cn) st_stream(cn + i1, (int)(unsigned)c1);
+            if (uni) st_stream(uni + i1, (int)(unsigned)(c1 >> 32));
+            if (jac) st_stream(jac + i1, __longlong_as_double((long long)j1));
+            if (aa) st_stream(aa + i1, __longlong_as_double((long long)a1));
+        }
     }
 }
 
