@@ -104,6 +104,40 @@ class _DeviceMemory(object):
                                          'data': (int(ptr), False), 'version': 2}
 
 
+def window_layout(n_total, columns=REFERENCE_COLUMNS, compact=True, derived=None):
+    """The memory plan of a ResultWindow (pure function; no device needed).
+
+    Returns a dict: 'columns' (what `dst` ends up with), 'derived' (what `dst` computes instead of
+    receiving), 'allocated' (the columns the window holds: the requested ones plus the cn / union
+    a derived jaccard needs), 'wire' (what a peer's kernels store), 'offsets' (byte offset of every
+    allocated column, struct of arrays, 256-byte aligned), 'nbytes', 'wire_bytes_per_pair'.
+    """
+    columns = tuple(columns)
+    bad = [c for c in columns if c not in ALL_COLUMNS]
+    if bad:
+        raise ValueError('unknown result columns %r' % (bad,))
+    # which columns `dst` derives instead of receiving.  Default ('pa',): 40 B per pair on the
+    # wire and nothing left to do after the peers' rows have landed, pa being a function of
+    # the pair ids alone; DERIVED_COLUMNS: 32 B on the wire, jaccard derived afterwards
+    derived = tuple(DEFAULT_DERIVED if derived is None else derived) if compact else ()
+    bad = [c for c in derived if c not in DERIVED_COLUMNS]
+    if bad:
+        raise ValueError('cannot derive %r on the destination' % (bad,))
+    derived = tuple(c for c in derived if c in columns)
+    alloc = list(columns)
+    for side in 'ub':                            # jaccard is derived from (cn, union) on `dst`
+        if side + '_jaccard' in derived:
+            alloc += [c for c in (side + '_cn', side + '_union') if c not in alloc]
+    offsets, at = {}, 0
+    for c in alloc:                              # struct of arrays, 256-byte aligned columns
+        offsets[c] = at
+        at += (_ITEMSIZE[_kind(c)] * max(int(n_total), 1) + 255) // 256 * 256
+    wire = tuple(c for c in alloc if c not in derived)
+    return {'columns': columns, 'derived': derived, 'allocated': tuple(alloc), 'wire': wire,
+            'offsets': offsets, 'nbytes': max(at, 256),
+            'wire_bytes_per_pair': sum(_ITEMSIZE[_kind(c)] for c in wire)}
+
+
 class ResultWindow(object):
     """The result table of a sharded scoring job: every column for all `n_total` pairs, resident
     on rank `dst`, writable by the scoring kernels of every rank (see the module docstring).
@@ -122,33 +156,16 @@ class ResultWindow(object):
         self._lib = _lib.load()
         self.device = graph.device
         self.n_total = int(n_total)
-        self.columns = tuple(columns)
-        bad = [c for c in self.columns if c not in ALL_COLUMNS]
-        if bad:
-            raise ValueError('unknown result columns %r' % (bad,))
+        plan = window_layout(self.n_total, columns, compact, derived)
+        self.columns = plan['columns']
         self.compact = bool(compact)
-        # which columns `dst` derives instead of receiving.  Default ('pa',): 40 B per pair on the
-        # wire and nothing left to do after the peers' rows have landed, pa being a function of
-        # the pair ids alone; DERIVED_COLUMNS: 32 B on the wire, jaccard derived afterwards
-        self.derived = tuple(DEFAULT_DERIVED if derived is None else derived) if self.compact else ()
-        bad = [c for c in self.derived if c not in DERIVED_COLUMNS]
-        if bad:
-            raise ValueError('cannot derive %r on the destination' % (bad,))
+        self.derived = plan['derived']
         self.graph = graph
-        alloc = list(self.columns)
-        if self.compact:                         # jaccard is derived from (cn, union) on `dst`
-            for side in 'ub':
-                if side + '_jaccard' in alloc and side + '_jaccard' in self.derived:
-                    alloc += [c for c in (side + '_cn', side + '_union') if c not in alloc]
-        self._alloc_columns = tuple(alloc)
+        self._alloc_columns = plan['allocated']
+        self.offsets, self.nbytes = plan['offsets'], plan['nbytes']
         self.dst = dst
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.offsets, at = {}, 0
-        for c in self._alloc_columns:               # struct of arrays, 256-byte aligned columns
-            self.offsets[c] = at
-            at += (_ITEMSIZE[_kind(c)] * max(self.n_total, 1) + 255) // 256 * 256
-        self.nbytes = max(at, 256)
         self._base = ctypes.c_void_p()
         self._owner = self.rank == dst
         dev = self.device.index or 0

@@ -157,3 +157,32 @@ def test_algorithmic_bytes_on_known_answer():
     assert ab['stream_user'] == 32 * 8 + 4 * sum(degv) + 8 * sum(u_cn[:8])
     assert ab['invalid'] == 64 and ab['pa'] == 80
     assert ab['total'] == ab['user'] + ab['business'] + ab['pa']
+
+
+def test_result_window_layout():
+    """The memory plan of the multi-GPU result window (pure host logic of dist.ResultWindow)."""
+    d = pkg('dist')
+    n = 1000
+    ref = d.window_layout(n)                                   # the seven reference columns, pa derived
+    assert ref['columns'] == d.REFERENCE_COLUMNS and ref['derived'] == ('pa',)
+    assert ref['allocated'] == d.REFERENCE_COLUMNS             # nothing extra is needed to derive pa
+    assert 'pa' not in ref['wire'] and ref['wire_bytes_per_pair'] == 40
+    # 32 bytes on the wire: jaccard derived too, which needs cn and union in the window
+    c32 = d.window_layout(n, derived=d.DERIVED_COLUMNS)
+    assert set(c32['wire']) == set(d.WIRE_COLUMNS) and c32['wire_bytes_per_pair'] == 32
+    assert {'u_union', 'b_union'} <= set(c32['allocated']) and 'u_union' not in c32['columns']
+    # everything stored by the kernels
+    full = d.window_layout(n, columns=d.ALL_COLUMNS, compact=False)
+    assert full['derived'] == () and full['wire_bytes_per_pair'] == 56
+    # a column that is not asked for is neither allocated nor derived
+    few = d.window_layout(n, columns=('u_cn', 'b_adamic'))
+    assert few['derived'] == () and few['allocated'] == ('u_cn', 'b_adamic') and few['wire_bytes_per_pair'] == 12
+    for plan in (ref, c32, full, few):
+        spans = sorted((plan['offsets'][c], {'cn': 4, 'union': 4}.get(c.split('_')[-1], 8) * n) for c in plan['allocated'])
+        assert all(o % 256 == 0 for o, _ in spans)
+        assert all(a + la <= b for (a, la), (b, _) in zip(spans, spans[1:]))      # columns do not overlap
+        assert spans[-1][0] + spans[-1][1] <= plan['nbytes']
+    with pytest.raises(ValueError):
+        d.window_layout(n, columns=('u_cn', 'nope'))
+    with pytest.raises(ValueError):
+        d.window_layout(n, derived=('u_cn',))
